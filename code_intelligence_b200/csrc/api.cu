@@ -1,0 +1,612 @@
+// C-ABI layer of libissue_emb_b200.so (declared in include/issue_emb_b200.h): handle management, weight
+// re-layout, workspace, and the launch sequence of the encoder hot path and the MLP head.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/issue_emb_b200.h"
+#include "kernels.h"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  const int code = (e == cudaErrorMemoryAllocation) ? IE_ERR_OOM : IE_ERR_CUDA;
+  if (e == cudaErrorMemoryAllocation) cudaGetLastError();  // clear the sticky-free OOM
+  return fail(code, "%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+}
+
+#define CK(expr)                                              \
+  do {                                                        \
+    cudaError_t _e = (expr);                                  \
+    if (_e != cudaSuccess) return cuda_fail(_e, #expr);       \
+  } while (0)
+
+inline long long round_up(long long x, long long m) { return (x + m - 1) / m * m; }
+
+// grow-only device buffer
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes, bool zero = false) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) { p = nullptr; return e; }
+    cap = bytes;
+    if (zero) {
+      // the handle's streams are non-blocking: make the (legacy-stream) memset complete before anyone uses it
+      e = cudaMemset(p, 0, bytes);
+      if (e != cudaSuccess) return e;
+      return cudaDeviceSynchronize();
+    }
+    return cudaSuccess;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct Layer {
+  int in = 0, out = 0;      // logical dims
+  int u = 0, n_cta = 0;     // hidden units per CTA, CTAs per step
+  int out_pad = 0;          // n_cta * u
+  int kin_pad = 0;          // padded K of the input projection
+  int kh_pad = 0;           // padded K of the recurrent projection
+  int bn = 0;               // GEMM N tile for the input projection
+  DevBuf w_ih, w_hh, bias;  // sliced layouts
+  bool loaded = false;
+};
+
+}  // namespace
+
+struct ie_encoder {
+  ie_config cfg{};
+  int num_sms = 148;
+  int e_pad = 0;  // emb_sz rounded up to 64
+  std::vector<Layer> layers;
+  DevBuf emb;  // bf16 [vocab, e_pad]
+  bool emb_loaded = false;
+  // workspace
+  DevBuf ids, lengths, x0, y[2], gx, c, pool_sum, pool_max, pool_last, out, raw, err;
+  long long y_ld = 0;
+  size_t y_bytes_zeroed = 0;
+  cudaStream_t own_stream = nullptr;
+  int64_t launches = 0;
+  std::mutex mu;
+};
+
+struct ie_mlp {
+  int device = 0;
+  int num_sms = 148;
+  std::vector<int> dims;
+  struct L {
+    int k_pad = 0, n_pad = 0, bn = 0;
+    DevBuf w, b;
+    bool loaded = false;
+  };
+  std::vector<L> layers;
+  DevBuf xf, act[2], probs;
+  long long act_ld = 0;
+  cudaStream_t own_stream = nullptr;
+  std::mutex mu;
+};
+
+namespace {
+
+int plan_layers(ie_encoder* h) {
+  const ie_config& c = h->cfg;
+  h->e_pad = static_cast<int>(round_up(c.emb_sz, 64));
+  h->layers.resize(c.n_layers);
+  int prev_pad = h->e_pad;
+  for (int l = 0; l < c.n_layers; ++l) {
+    Layer& L = h->layers[l];
+    L.in = (l == 0) ? c.emb_sz : c.n_hid;
+    L.out = (l == c.n_layers - 1) ? c.emb_sz : c.n_hid;
+    // u hidden units per CTA: multiple of 4, as many CTAs as fit on the SMs (one wave)
+    L.u = 4 * static_cast<int>((L.out + 4ll * h->num_sms - 1) / (4ll * h->num_sms));
+    if (L.u > 32) return fail(IE_ERR_INVALID, "hidden size %d too large for %d SMs", L.out, h->num_sms);
+    L.n_cta = (L.out + L.u - 1) / L.u;
+    L.out_pad = L.n_cta * L.u;
+    L.kin_pad = prev_pad;
+    L.kh_pad = static_cast<int>(round_up(L.out_pad, 64));
+    prev_pad = L.kh_pad;
+    // largest multiple of 16 <= 256 dividing 4*out_pad
+    const int n = 4 * L.out_pad;
+    L.bn = 16;
+    for (int b = 256; b >= 16; b -= 16)
+      if (n % b == 0) { L.bn = b; break; }
+  }
+  return IE_OK;
+}
+
+// torch gate-major rows [4*out] -> sliced rows [cta][unit][gate]; -1 marks zero padding rows
+std::vector<int> slice_perm(const Layer& L) {
+  std::vector<int> perm(4 * static_cast<size_t>(L.out_pad));
+  for (int j = 0; j < L.n_cta; ++j)
+    for (int i = 0; i < L.u; ++i)
+      for (int g = 0; g < 4; ++g) {
+        const int unit = j * L.u + i;
+        perm[(static_cast<size_t>(j) * L.u + i) * 4 + g] = unit < L.out ? g * L.out + unit : -1;
+      }
+  return perm;
+}
+
+int upload_sliced(const float* host, int rows_src, int cols, const std::vector<int>& perm, int ld_dst, DevBuf& dst,
+                  cudaStream_t s) {
+  DevBuf tmp, dperm;
+  CK(tmp.reserve(static_cast<size_t>(rows_src) * cols * sizeof(float)));
+  CK(dperm.reserve(perm.size() * sizeof(int)));
+  CK(cudaMemcpyAsync(tmp.p, host, static_cast<size_t>(rows_src) * cols * sizeof(float), cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(dperm.p, perm.data(), perm.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+  CK(dst.reserve(perm.size() * static_cast<size_t>(ld_dst) * sizeof(__nv_bfloat16)));
+  CK(ie::launch_convert_rows(tmp.as<float>(), cols, cols, dperm.as<int>(), static_cast<int>(perm.size()),
+                             dst.as<__nv_bfloat16>(), ld_dst, s));
+  CK(cudaStreamSynchronize(s));
+  tmp.release();
+  dperm.release();
+  return IE_OK;
+}
+
+int ensure_workspace(ie_encoder* h, int b_pad, int T, bool want_raw) {
+  const ie_config& c = h->cfg;
+  long long max_out_pad = 0, max_kh = 0;
+  for (const Layer& L : h->layers) {
+    max_out_pad = std::max<long long>(max_out_pad, L.out_pad);
+    max_kh = std::max<long long>(max_kh, L.kh_pad);
+  }
+  const long long rows = static_cast<long long>(T) * b_pad;
+  CK(h->ids.reserve(static_cast<size_t>(IE_MAX_BATCH) * T * sizeof(int64_t)));
+  CK(h->lengths.reserve(IE_MAX_BATCH * sizeof(int)));
+  CK(h->err.reserve(sizeof(int), true));
+  CK(h->x0.reserve(static_cast<size_t>(rows) * h->e_pad * sizeof(__nv_bfloat16)));
+  // hidden-state rings: (T+1) slots of b_pad rows; slot 0 and the K padding columns must be zero
+  h->y_ld = max_kh;
+  const size_t ybytes = static_cast<size_t>(rows + b_pad) * max_kh * sizeof(__nv_bfloat16);
+  for (int i = 0; i < 2; ++i) CK(h->y[i].reserve(ybytes, /*zero=*/true));
+  CK(h->gx.reserve(static_cast<size_t>(rows) * 4 * max_out_pad * sizeof(float)));
+  CK(h->c.reserve(static_cast<size_t>(IE_MAX_BATCH) * max_out_pad * sizeof(float)));
+  const size_t pb = static_cast<size_t>(IE_MAX_BATCH) * max_out_pad * sizeof(float);
+  CK(h->pool_sum.reserve(pb));
+  CK(h->pool_max.reserve(pb));
+  CK(h->pool_last.reserve(pb));
+  CK(h->out.reserve(static_cast<size_t>(IE_MAX_BATCH) * 3 * c.emb_sz * sizeof(float)));
+  if (want_raw) CK(h->raw.reserve(static_cast<size_t>(b_pad) * T * h->layers.back().out_pad * sizeof(float)));
+  return IE_OK;
+}
+
+// the launch sequence shared by encode (pooled) and raw_features
+int run_encoder(ie_encoder* h, const int64_t* ids, const int32_t* lengths, int B, int T, float* out, float* raw_out,
+                int flags, cudaStream_t s) {
+  const ie_config& c = h->cfg;
+  if (!h->emb_loaded) return fail(IE_ERR_STATE, "embedding not loaded");
+  for (const Layer& L : h->layers)
+    if (!L.loaded) return fail(IE_ERR_STATE, "LSTM layer weights not loaded");
+  if (B < 1 || B > IE_MAX_BATCH) return fail(IE_ERR_INVALID, "B=%d outside [1,%d]", B, IE_MAX_BATCH);
+  if (T < 1) return fail(IE_ERR_INVALID, "T=%d must be >= 1", T);
+  if (ids == nullptr || (out == nullptr && raw_out == nullptr)) return fail(IE_ERR_INVALID, "null pointer");
+  const bool dev = (flags & IE_FLAG_DEVICE_PTRS) != 0;
+  const bool pooled = out != nullptr;
+  const int b_pad = B <= 128 ? 128 : 256;
+  if (static_cast<long long>(b_pad) * T > (1ll << 21))
+    return fail(IE_ERR_OOM, "B_pad*T = %lld tokens exceeds the workspace cap; use a smaller batch",
+                static_cast<long long>(b_pad) * T);
+  CK(cudaSetDevice(c.device));
+  int rc = ensure_workspace(h, b_pad, T, raw_out != nullptr);
+  if (rc != IE_OK) return rc;
+
+  // lengths: validate on the host when we can; padded rows get length 1
+  std::vector<int> len_host(IE_MAX_BATCH, 1);
+  if (pooled) {
+    if (lengths == nullptr) return fail(IE_ERR_INVALID, "lengths is null");
+    if (!dev) {
+      for (int b = 0; b < B; ++b) {
+        if (lengths[b] < 1 || lengths[b] > T)
+          return fail(IE_ERR_INVALID, "lengths[%d]=%d outside [1,%d]", b, lengths[b], T);
+        len_host[b] = lengths[b];
+      }
+      CK(cudaMemcpyAsync(h->lengths.p, len_host.data(), IE_MAX_BATCH * sizeof(int), cudaMemcpyHostToDevice, s));
+    } else {
+      CK(cudaMemcpyAsync(h->lengths.p, len_host.data(), IE_MAX_BATCH * sizeof(int), cudaMemcpyHostToDevice, s));
+      CK(cudaMemcpyAsync(h->lengths.p, lengths, B * sizeof(int), cudaMemcpyDeviceToDevice, s));
+    }
+  }
+  const int64_t* ids_dev = ids;
+  if (!dev) {
+    CK(cudaMemcpyAsync(h->ids.p, ids, static_cast<size_t>(B) * T * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+    ids_dev = h->ids.as<int64_t>();
+  }
+
+  CK(ie::launch_embed_gather(ids_dev, B, T, b_pad, h->emb.as<__nv_bfloat16>(), c.vocab_sz, h->e_pad,
+                             h->x0.as<__nv_bfloat16>(), h->e_pad, c.pad_idx, h->err.as<int>(), s));
+  h->launches++;
+
+  const long long rows = static_cast<long long>(T) * b_pad;
+  int cur = 0;
+  const __nv_bfloat16* layer_in = h->x0.as<__nv_bfloat16>();
+  long long layer_in_ld = h->e_pad;
+  for (int l = 0; l < c.n_layers; ++l) {
+    Layer& L = h->layers[l];
+    const bool last = (l == c.n_layers - 1);
+    // hoisted input projection over all T*b_pad rows
+    ie::GemmArgs g{};
+    g.a = layer_in;
+    g.lda = layer_in_ld;
+    g.b = L.w_ih.as<__nv_bfloat16>();
+    g.ldb = L.kin_pad;
+    g.d = h->gx.p;
+    g.ldd = 4ll * L.out_pad;
+    g.bias = L.bias.as<float>();
+    g.m_pad = static_cast<int>(rows);
+    g.n_pad = 4 * L.out_pad;
+    g.k_pad = L.kin_pad;
+    g.m_store = static_cast<int>(rows);
+    g.n_store = 4 * L.out_pad;
+    g.bn = L.bn;
+    g.act = 0;
+    g.out_bf16 = 0;
+    g.num_sms = h->num_sms;
+    CK(ie::launch_gemm_bf16(g, s));
+    h->launches++;
+
+    // recurrence
+    ie::LstmStepArgs a{};
+    __nv_bfloat16* ybuf = h->y[cur].as<__nv_bfloat16>();
+    CK(ie::make_tmap_bf16_2d(&a.tm_h, ybuf, L.kh_pad, static_cast<uint64_t>(rows + b_pad), h->y_ld, 64, 128));
+    CK(ie::make_tmap_bf16_2d(&a.tm_w, L.w_hh.p, L.kh_pad, 4ull * L.out_pad, L.kh_pad, 64, 4 * L.u));
+    a.gx = h->gx.as<float>();
+    a.c = h->c.as<float>();
+    a.y = ybuf;
+    a.raw = (last && raw_out != nullptr) ? h->raw.as<float>() : nullptr;
+    a.pool_sum = (last && pooled) ? h->pool_sum.as<float>() : nullptr;
+    a.pool_max = h->pool_max.as<float>();
+    a.pool_last = h->pool_last.as<float>();
+    a.lengths = h->lengths.as<int>();
+    a.T = T;
+    a.b_pad = b_pad;
+    a.u = L.u;
+    a.n_cta = L.n_cta;
+    a.out_pad = L.out_pad;
+    a.kh_pad = L.kh_pad;
+    a.ldy = h->y_ld;
+    a.raw_ld = L.out_pad;
+    for (int t = 0; t < T; ++t) {
+      a.t = t;
+      CK(ie::launch_lstm_step(a, s));
+    }
+    h->launches += T;
+    layer_in = ybuf + static_cast<long long>(b_pad) * h->y_ld;  // slot 1 onwards
+    layer_in_ld = h->y_ld;
+    cur ^= 1;
+  }
+
+  const Layer& LL = h->layers.back();
+  if (pooled) {
+    float* out_dev = dev ? out : h->out.as<float>();
+    CK(ie::launch_pool_finalize(h->pool_sum.as<float>(), h->pool_max.as<float>(), h->pool_last.as<float>(),
+                                h->lengths.as<int>(), B, c.emb_sz, LL.out_pad, out_dev, s));
+    h->launches++;
+    if (!dev)
+      CK(cudaMemcpyAsync(out, out_dev, static_cast<size_t>(B) * 3 * c.emb_sz * sizeof(float), cudaMemcpyDeviceToHost, s));
+  }
+  if (raw_out != nullptr) {
+    // raw workspace is [b_pad, T, out_pad]; compact to [B, T, emb_sz]
+    CK(cudaMemcpy2DAsync(raw_out, static_cast<size_t>(c.emb_sz) * sizeof(float), h->raw.p,
+                         static_cast<size_t>(LL.out_pad) * sizeof(float), static_cast<size_t>(c.emb_sz) * sizeof(float),
+                         static_cast<size_t>(B) * T, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
+  }
+  if (!dev) {
+    int err_host = 0;
+    CK(cudaMemcpyAsync(&err_host, h->err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (err_host != 0) {
+      cudaMemsetAsync(h->err.p, 0, sizeof(int), s);
+      return fail(IE_ERR_TOKEN, "token id outside [0,%d) in ids", c.vocab_sz);
+    }
+  }
+  return IE_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ie_version(void) { return 100; }
+
+const char* ie_last_error(void) { return g_last_error.c_str(); }
+
+int ie_encoder_create(const ie_config* cfg, ie_encoder** out) {
+  if (cfg == nullptr || out == nullptr) return fail(IE_ERR_INVALID, "null argument");
+  if (cfg->n_layers < 1 || cfg->n_layers > 16 || cfg->emb_sz < 1 || cfg->n_hid < 1 || cfg->vocab_sz < 1 ||
+      cfg->pad_idx < 0 || cfg->pad_idx >= cfg->vocab_sz)
+    return fail(IE_ERR_INVALID, "bad encoder config");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(IE_ERR_CUDA, "no CUDA device available (%s): this library has no CPU fallback",
+                cudaGetErrorString(e));
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(IE_ERR_INVALID, "device %d not in [0,%d)", cfg->device, ndev);
+  CK(cudaSetDevice(cfg->device));
+  int major = 0, sms = 0;
+  CK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, cfg->device));
+  CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device));
+  if (major != 10) return fail(IE_ERR_CUDA, "device compute capability %d.x is not sm_100 (B200)", major);
+  ie_encoder* h = new ie_encoder();
+  h->cfg = *cfg;
+  h->num_sms = sms;
+  int rc = plan_layers(h);
+  if (rc != IE_OK) { delete h; return rc; }
+  e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { delete h; return cuda_fail(e, "cudaStreamCreate"); }
+  *out = h;
+  return IE_OK;
+}
+
+void ie_encoder_destroy(ie_encoder* h) {
+  if (h == nullptr) return;
+  cudaSetDevice(h->cfg.device);
+  cudaDeviceSynchronize();
+  for (Layer& L : h->layers) { L.w_ih.release(); L.w_hh.release(); L.bias.release(); }
+  DevBuf* bufs[] = {&h->emb, &h->ids, &h->lengths, &h->x0, &h->y[0], &h->y[1], &h->gx, &h->c, &h->pool_sum,
+                    &h->pool_max, &h->pool_last, &h->out, &h->raw, &h->err};
+  for (DevBuf* b : bufs) b->release();
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h;
+}
+
+int ie_encoder_load_embedding(ie_encoder* h, const float* emb) {
+  if (h == nullptr || emb == nullptr) return fail(IE_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> lk(h->mu);
+  CK(cudaSetDevice(h->cfg.device));
+  std::vector<int> ident(h->cfg.vocab_sz);
+  for (int i = 0; i < h->cfg.vocab_sz; ++i) ident[i] = i;
+  int rc = upload_sliced(emb, h->cfg.vocab_sz, h->cfg.emb_sz, ident, h->e_pad, h->emb, h->own_stream);
+  if (rc != IE_OK) return rc;
+  h->emb_loaded = true;
+  return IE_OK;
+}
+
+int ie_encoder_load_layer(ie_encoder* h, int32_t layer, const float* w_ih, const float* w_hh, const float* b_ih,
+                          const float* b_hh) {
+  if (h == nullptr || w_ih == nullptr || w_hh == nullptr || b_ih == nullptr || b_hh == nullptr)
+    return fail(IE_ERR_INVALID, "null argument");
+  if (layer < 0 || layer >= h->cfg.n_layers) return fail(IE_ERR_INVALID, "layer %d out of range", layer);
+  std::lock_guard<std::mutex> lk(h->mu);
+  CK(cudaSetDevice(h->cfg.device));
+  Layer& L = h->layers[layer];
+  const std::vector<int> perm = slice_perm(L);
+  int rc = upload_sliced(w_ih, 4 * L.out, L.in, perm, L.kin_pad, L.w_ih, h->own_stream);
+  if (rc != IE_OK) return rc;
+  rc = upload_sliced(w_hh, 4 * L.out, L.out, perm, L.kh_pad, L.w_hh, h->own_stream);
+  if (rc != IE_OK) return rc;
+  std::vector<float> bias(perm.size());
+  for (size_t r = 0; r < perm.size(); ++r) bias[r] = perm[r] < 0 ? 0.0f : b_ih[perm[r]] + b_hh[perm[r]];
+  CK(L.bias.reserve(bias.size() * sizeof(float)));
+  CK(cudaMemcpy(L.bias.p, bias.data(), bias.size() * sizeof(float), cudaMemcpyHostToDevice));
+  L.loaded = true;
+  return IE_OK;
+}
+
+int ie_encoder_encode(ie_encoder* h, const int64_t* ids, const int32_t* lengths, int32_t B, int32_t T, float* out,
+                      int32_t flags, void* stream) {
+  if (h == nullptr) return fail(IE_ERR_INVALID, "null handle");
+  if (out == nullptr) return fail(IE_ERR_INVALID, "out is null");
+  std::lock_guard<std::mutex> lk(h->mu);
+  cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : h->own_stream;
+  return run_encoder(h, ids, lengths, B, T, out, nullptr, flags, s);
+}
+
+int ie_encoder_raw_features(ie_encoder* h, const int64_t* ids, int32_t B, int32_t T, float* raw, int32_t flags,
+                            void* stream) {
+  if (h == nullptr) return fail(IE_ERR_INVALID, "null handle");
+  if (raw == nullptr) return fail(IE_ERR_INVALID, "raw is null");
+  std::lock_guard<std::mutex> lk(h->mu);
+  cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : h->own_stream;
+  return run_encoder(h, ids, nullptr, B, T, nullptr, raw, flags, s);
+}
+
+int64_t ie_encoder_launch_count(const ie_encoder* h) { return h ? h->launches : 0; }
+
+// ---------------------------------------------------------------------------------------------
+// MLP head
+// ---------------------------------------------------------------------------------------------
+int ie_mlp_create(int32_t n_layers, const int32_t* dims, int32_t device, ie_mlp** out) {
+  if (dims == nullptr || out == nullptr || n_layers < 1 || n_layers > 16) return fail(IE_ERR_INVALID, "bad argument");
+  for (int i = 0; i <= n_layers; ++i)
+    if (dims[i] < 1) return fail(IE_ERR_INVALID, "dims[%d]=%d", i, dims[i]);
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(IE_ERR_CUDA, "no CUDA device available (%s): this library has no CPU fallback",
+                cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return fail(IE_ERR_INVALID, "device %d not in [0,%d)", device, ndev);
+  CK(cudaSetDevice(device));
+  int major = 0, sms = 0;
+  CK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+  CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  if (major != 10) return fail(IE_ERR_CUDA, "device compute capability %d.x is not sm_100 (B200)", major);
+  ie_mlp* m = new ie_mlp();
+  m->device = device;
+  m->num_sms = sms;
+  m->dims.assign(dims, dims + n_layers + 1);
+  m->layers.resize(n_layers);
+  long long ld = 64;
+  for (int l = 0; l < n_layers; ++l) {
+    ie_mlp::L& L = m->layers[l];
+    L.k_pad = static_cast<int>(round_up(dims[l], 64));
+    const int n16 = static_cast<int>(round_up(dims[l + 1], 16));
+    L.bn = n16 >= 128 ? 128 : n16;
+    L.n_pad = static_cast<int>(round_up(dims[l + 1], L.bn));
+    ld = std::max<long long>(ld, round_up(std::max(L.n_pad, L.k_pad), 64));
+  }
+  m->act_ld = ld;
+  e = cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { delete m; return cuda_fail(e, "cudaStreamCreate"); }
+  *out = m;
+  return IE_OK;
+}
+
+int ie_mlp_load_layer(ie_mlp* m, int32_t layer, const float* coef, const float* intercept) {
+  if (m == nullptr || coef == nullptr || intercept == nullptr) return fail(IE_ERR_INVALID, "null argument");
+  if (layer < 0 || layer >= static_cast<int>(m->layers.size())) return fail(IE_ERR_INVALID, "layer out of range");
+  std::lock_guard<std::mutex> lk(m->mu);
+  CK(cudaSetDevice(m->device));
+  ie_mlp::L& L = m->layers[layer];
+  const int fan_in = m->dims[layer], fan_out = m->dims[layer + 1];
+  // sklearn coefs_[l] is [fan_in, fan_out]; the GEMM wants B = [fan_out rows, fan_in] (K-major)
+  std::vector<float> wt(static_cast<size_t>(fan_out) * fan_in);
+  for (int i = 0; i < fan_in; ++i)
+    for (int o = 0; o < fan_out; ++o) wt[static_cast<size_t>(o) * fan_in + i] = coef[static_cast<size_t>(i) * fan_out + o];
+  std::vector<int> perm(L.n_pad);
+  for (int r = 0; r < L.n_pad; ++r) perm[r] = r < fan_out ? r : -1;
+  int rc = upload_sliced(wt.data(), fan_out, fan_in, perm, L.k_pad, L.w, m->own_stream);
+  if (rc != IE_OK) return rc;
+  std::vector<float> b(L.n_pad, 0.0f);
+  std::copy(intercept, intercept + fan_out, b.begin());
+  CK(L.b.reserve(b.size() * sizeof(float)));
+  CK(cudaMemcpy(L.b.p, b.data(), b.size() * sizeof(float), cudaMemcpyHostToDevice));
+  L.loaded = true;
+  return IE_OK;
+}
+
+int ie_mlp_predict_proba(ie_mlp* m, const float* X, int32_t n, float* probs, int32_t flags, void* stream) {
+  if (m == nullptr || X == nullptr || probs == nullptr) return fail(IE_ERR_INVALID, "null argument");
+  if (n < 1) return fail(IE_ERR_INVALID, "n=%d", n);
+  for (const auto& L : m->layers)
+    if (!L.loaded) return fail(IE_ERR_STATE, "MLP layer weights not loaded");
+  std::lock_guard<std::mutex> lk(m->mu);
+  CK(cudaSetDevice(m->device));
+  cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : m->own_stream;
+  const bool dev = (flags & IE_FLAG_DEVICE_PTRS) != 0;
+  const int nl = static_cast<int>(m->layers.size());
+  const int d_in = m->dims[0], n_labels = m->dims[nl];
+  const int chunk = 1 << 16;
+  const ie_mlp::L& LL = m->layers[nl - 1];
+  CK(m->act[0].reserve(static_cast<size_t>(chunk) * m->act_ld * sizeof(__nv_bfloat16), true));
+  CK(m->act[1].reserve(static_cast<size_t>(chunk) * m->act_ld * sizeof(__nv_bfloat16), true));
+  CK(m->probs.reserve(static_cast<size_t>(chunk) * LL.n_pad * sizeof(float)));
+  if (!dev) CK(m->xf.reserve(static_cast<size_t>(chunk) * d_in * sizeof(float)));
+  for (long long r0 = 0; r0 < n; r0 += chunk) {
+    const int rows = static_cast<int>(std::min<long long>(chunk, n - r0));
+    const int m_pad = static_cast<int>(round_up(rows, 128));
+    const float* xsrc = X + r0 * d_in;
+    if (!dev) {
+      CK(cudaMemcpyAsync(m->xf.p, xsrc, static_cast<size_t>(rows) * d_in * sizeof(float), cudaMemcpyHostToDevice, s));
+      xsrc = m->xf.as<float>();
+    }
+    // f32 -> bf16, K padded with zeros (rows beyond `rows` keep stale finite data; they are never stored)
+    CK(ie::launch_convert_rows(xsrc, d_in, d_in, nullptr, rows, m->act[0].as<__nv_bfloat16>(), m->act_ld, s));
+    int cur = 0;
+    for (int l = 0; l < nl; ++l) {
+      const ie_mlp::L& L = m->layers[l];
+      const bool last = (l == nl - 1);
+      ie::GemmArgs g{};
+      g.a = m->act[cur].as<__nv_bfloat16>();
+      g.lda = m->act_ld;
+      g.b = L.w.as<__nv_bfloat16>();
+      g.ldb = L.k_pad;
+      g.bias = L.b.as<float>();
+      g.m_pad = m_pad;
+      g.n_pad = L.n_pad;
+      g.k_pad = L.k_pad;
+      g.m_store = rows;
+      g.n_store = L.n_pad;
+      g.bn = L.bn;
+      g.num_sms = m->num_sms;
+      if (last) {
+        g.d = m->probs.p;
+        g.ldd = L.n_pad;
+        g.act = 2;
+        g.out_bf16 = 0;
+      } else {
+        g.d = m->act[cur ^ 1].p;
+        g.ldd = m->act_ld;
+        g.act = 1;
+        g.out_bf16 = 1;
+      }
+      CK(ie::launch_gemm_bf16(g, s));
+      cur ^= 1;
+    }
+    CK(cudaMemcpy2DAsync(probs + r0 * n_labels, static_cast<size_t>(n_labels) * sizeof(float), m->probs.p,
+                         static_cast<size_t>(LL.n_pad) * sizeof(float), static_cast<size_t>(n_labels) * sizeof(float),
+                         rows, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
+    if (!dev) CK(cudaStreamSynchronize(s));  // xf is reused by the next chunk
+  }
+  return IE_OK;
+}
+
+void ie_mlp_destroy(ie_mlp* m) {
+  if (m == nullptr) return;
+  cudaSetDevice(m->device);
+  cudaDeviceSynchronize();
+  for (auto& L : m->layers) { L.w.release(); L.b.release(); }
+  m->xf.release(); m->act[0].release(); m->act[1].release(); m->probs.release();
+  if (m->own_stream) cudaStreamDestroy(m->own_stream);
+  delete m;
+}
+
+int ie_debug_gemm(const float* a, const float* b, const float* bias, int32_t M, int32_t N, int32_t K, int32_t act,
+                  float* d, int32_t device) {
+  if (a == nullptr || b == nullptr || d == nullptr || M < 1 || N < 1 || K < 1) return fail(IE_ERR_INVALID, "bad argument");
+  CK(cudaSetDevice(device));
+  int sms = 148;
+  CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  const int m_pad = static_cast<int>(round_up(M, 128)), k_pad = static_cast<int>(round_up(K, 64));
+  const int n16 = static_cast<int>(round_up(N, 16));
+  int bn = 16;
+  if (n16 >= 240 && n16 % 240 == 0) bn = 240;
+  else if (n16 >= 128) bn = 128;
+  else bn = n16;
+  const int n_pad = static_cast<int>(round_up(N, bn));
+  DevBuf fa, fb, ba, bb, dd, db;
+  cudaStream_t s = nullptr;
+  CK(fa.reserve(static_cast<size_t>(M) * K * 4));
+  CK(fb.reserve(static_cast<size_t>(N) * K * 4));
+  CK(ba.reserve(static_cast<size_t>(m_pad) * k_pad * 2, true));
+  CK(bb.reserve(static_cast<size_t>(n_pad) * k_pad * 2, true));
+  CK(dd.reserve(static_cast<size_t>(m_pad) * n_pad * 4));
+  CK(cudaMemcpy(fa.p, a, static_cast<size_t>(M) * K * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(fb.p, b, static_cast<size_t>(N) * K * 4, cudaMemcpyHostToDevice));
+  CK(ie::launch_convert_rows(fa.as<float>(), K, K, nullptr, M, ba.as<__nv_bfloat16>(), k_pad, s));
+  CK(ie::launch_convert_rows(fb.as<float>(), K, K, nullptr, N, bb.as<__nv_bfloat16>(), k_pad, s));
+  if (bias) {
+    std::vector<float> bp(n_pad, 0.0f);
+    std::copy(bias, bias + N, bp.begin());
+    CK(db.reserve(n_pad * 4));
+    CK(cudaMemcpy(db.p, bp.data(), n_pad * 4, cudaMemcpyHostToDevice));
+  }
+  ie::GemmArgs g{};
+  g.a = ba.as<__nv_bfloat16>(); g.lda = k_pad;
+  g.b = bb.as<__nv_bfloat16>(); g.ldb = k_pad;
+  g.d = dd.p; g.ldd = n_pad;
+  g.bias = bias ? db.as<float>() : nullptr;
+  g.m_pad = m_pad; g.n_pad = n_pad; g.k_pad = k_pad;
+  g.m_store = M; g.n_store = n_pad; g.bn = bn; g.act = act; g.out_bf16 = 0; g.num_sms = sms;
+  CK(ie::launch_gemm_bf16(g, s));
+  CK(cudaMemcpy2D(d, static_cast<size_t>(N) * 4, dd.p, static_cast<size_t>(n_pad) * 4, static_cast<size_t>(N) * 4, M,
+                  cudaMemcpyDeviceToHost));
+  fa.release(); fb.release(); ba.release(); bb.release(); dd.release(); db.release();
+  return IE_OK;
+}
+
+}  // extern "C"

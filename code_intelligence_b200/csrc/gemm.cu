@@ -1,0 +1,237 @@
+// Persistent tcgen05 GEMM:  D[M, N] = act(A[M, K] * B[N, K]^T + bias[N])
+//
+//   A, B : bf16, K-major (row-major with K contiguous), K padded to a multiple of 64 and physically
+//          zero-filled, rows padded to whole tiles -> no reliance on TMA out-of-bounds fill.
+//   D    : f32 or bf16, row-major with leading dimension ldd.
+//
+// Used for (i) the hoisted LSTM input projections  Gx = X * W_ih^T + (b_ih + b_hh)  over all T*B rows at
+// once (the non-recurrent 46 % of the encoder FLOPs; reference: fastai AWD_LSTM -> torch nn.LSTM called at
+// Issue_Embeddings/flask_app/inference.py:57,68) and (ii) the Label_Microservice MLP layers
+// (py/label_microservice/mlp.py:63 -> sklearn predict_proba).
+//
+// Structure (one CTA per SM, 256 threads, warp-specialised):
+//   warp 0      TMA producer: A tile 128x64 and B tile bn x 64 per stage, 128B swizzle, mbarrier complete_tx
+//   warp 1      UMMA issuer : tcgen05.mma kind::f16 M=128 N=bn K=16, accumulators in TMEM (double buffered)
+//   warp 2      TMEM allocator
+//   warps 4..7  epilogue    : tcgen05.ld -> +bias -> activation -> global stores; overlaps the next tile's MMAs
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace ie {
+
+namespace {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;  // 64 bf16 = 128 B = one swizzle atom
+constexpr int kGemmThreads = 256;
+
+template <typename OutT, int ACT>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, OutT* __restrict__ D,
+                 const float* __restrict__ bias, int m_store, int n_store, long long ldd, int num_m_blocks,
+                 int num_n_blocks, int num_k_blocks, int bn, int stages, int panel) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+
+  const uint32_t a_bytes = kBlockM * kBlockK * 2;
+  const uint32_t b_bytes = static_cast<uint32_t>(bn) * kBlockK * 2;
+  const uint32_t stage_bytes = a_bytes + b_bytes;  // bn % 8 == 0 -> multiple of 1024
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(stages) * stage_bytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + stages;
+  uint64_t* tfull_bar = bars + 2 * stages;
+  uint64_t* tempty_bar = bars + 2 * stages + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * stages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_tiles = num_m_blocks * num_n_blocks;
+  const int panel_tiles = panel * num_n_blocks;
+  // tile -> (m_blk, n_blk): m fastest inside a panel of `panel` m-blocks, then n, then next panel, so that
+  // the CTAs running together share B tiles and the A panel stays L2 resident across the n sweep.
+  auto decode = [&](int tile, int& m_blk, int& n_blk) {
+    const int p = tile / panel_tiles;
+    const int r = tile - p * panel_tiles;
+    const int m0 = p * panel;
+    const int mcnt = min(panel, num_m_blocks - m0);
+    n_blk = r / mcnt;
+    m_blk = m0 + (r - n_blk * mcnt);
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int m_blk, n_blk;
+        decode(tile, m_blk, n_blk);
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
+          mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
+          tma_load_2d(sa, &tmA, &full_bar[stage], kb * kBlockK, m_blk * kBlockM, kEvictNormal);
+          tma_load_2d(sa + a_bytes, &tmB, &full_bar[stage], kb * kBlockK, n_blk * bn, kEvictLast);
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(kBlockM, bn);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * bn);
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
+          const uint64_t da = umma_desc_sw128(sa);
+          const uint64_t db = umma_desc_sw128(sa + a_bytes);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            // advance 16 bf16 = 32 B inside the swizzle atom: +2 in the (addr >> 4) field
+            umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp - 4;  // TMEM lane quarter == warp % 4
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int m_blk, n_blk;
+      decode(tile, m_blk, n_blk);
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const int row = m_blk * kBlockM + q * 32 + lane;
+      const bool row_ok = row < m_store;
+      OutT* drow = D + static_cast<long long>(row) * ldd;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * bn);
+      for (int c = 0; c < bn; c += 16) {
+        uint32_t r[16];
+        tmem_ld16(taddr + c, r);
+        tmem_ld_wait();
+        const int n = n_blk * bn + c;
+        if (row_ok && n < n_store) {
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float x = __uint_as_float(r[j]);
+            if (bias != nullptr) x += __ldg(bias + n + j);
+            if (ACT == 1) x = fmaxf(x, 0.0f);
+            if (ACT == 2) x = sigmoid_acc(x);
+            v[j] = x;
+          }
+          if constexpr (sizeof(OutT) == 4) {
+            float4* dst = reinterpret_cast<float4*>(drow + n);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else {
+            uint4* dst = reinterpret_cast<uint4*>(drow + n);
+            dst[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                                pack_bf16x2(v[6], v[7]));
+            dst[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]),
+                                pack_bf16x2(v[14], v[15]));
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace
+
+size_t gemm_smem_bytes(int bn, int stages) {
+  return 1024 + static_cast<size_t>(stages) * (kBlockM * kBlockK * 2 + bn * kBlockK * 2) + (2 * stages + 4) * 8 + 16;
+}
+
+// Launch.  a: [m_pad rows, k_pad] bf16 (m_pad % 128 == 0, k_pad % 64 == 0); b: [n_pad rows, k_pad] bf16 with
+// n_pad % bn == 0.  Writes D rows < m_store and columns < n_store (n_store % 16 == 0).
+cudaError_t launch_gemm_bf16(const GemmArgs& g, cudaStream_t stream) {
+  if (g.m_pad % kBlockM || g.k_pad % kBlockK || g.bn % 16 || g.bn < 16 || g.bn > 256 || g.n_pad % g.bn ||
+      g.n_store % 16)
+    return cudaErrorInvalidValue;
+  CUtensorMap tmA, tmB;
+  cudaError_t e = make_tmap_bf16_2d(&tmA, g.a, g.k_pad, g.m_pad, g.lda, kBlockK, kBlockM);
+  if (e != cudaSuccess) return e;
+  e = make_tmap_bf16_2d(&tmB, g.b, g.k_pad, g.n_pad, g.ldb, kBlockK, g.bn);
+  if (e != cudaSuccess) return e;
+
+  int stages = 6;
+  while (stages > 2 && gemm_smem_bytes(g.bn, stages) > 227 * 1024) --stages;
+  const size_t smem = gemm_smem_bytes(g.bn, stages);
+  const int num_m_blocks = g.m_pad / kBlockM;
+  const int num_n_blocks = g.n_pad / g.bn;
+  const int num_k_blocks = g.k_pad / kBlockK;
+  const int num_tiles = num_m_blocks * num_n_blocks;
+  const int sms = g.num_sms > 0 ? g.num_sms : 148;
+  const int grid = num_tiles < sms ? num_tiles : sms;
+  int panel = sms / 2;
+  if (panel < 1) panel = 1;
+
+#define IE_LAUNCH(OUT, ACT)                                                                                        \
+  do {                                                                                                             \
+    auto kfn = gemm_bf16_kernel<OUT, ACT>;                                                                         \
+    e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));            \
+    if (e != cudaSuccess) return e;                                                                                \
+    kfn<<<grid, kGemmThreads, smem, stream>>>(tmA, tmB, reinterpret_cast<OUT*>(g.d), g.bias, g.m_store, g.n_store, \
+                                              g.ldd, num_m_blocks, num_n_blocks, num_k_blocks, g.bn, stages, panel); \
+  } while (0)
+
+  if (g.out_bf16) {
+    if (g.act == 0) IE_LAUNCH(__nv_bfloat16, 0);
+    else if (g.act == 1) IE_LAUNCH(__nv_bfloat16, 1);
+    else IE_LAUNCH(__nv_bfloat16, 2);
+  } else {
+    if (g.act == 0) IE_LAUNCH(float, 0);
+    else if (g.act == 1) IE_LAUNCH(float, 1);
+    else IE_LAUNCH(float, 2);
+  }
+#undef IE_LAUNCH
+  return cudaGetLastError();
+}
+
+}  // namespace ie

@@ -1,0 +1,70 @@
+// Internal launch interfaces between the C-ABI layer (api.cu) and the sm_100a kernels.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace ie {
+
+// ---- TMA descriptor helper (tmap.cu) ---------------------------------------------------------
+// 2-D bf16 tensor, inner (contiguous) dimension `inner` elements, `rows` rows, row pitch `ld` elements,
+// box {box_inner, box_rows}, 128-byte swizzle (box_inner must be 64).
+cudaError_t make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t rows, uint64_t ld,
+                              uint32_t box_inner, uint32_t box_rows);
+
+// ---- GEMM (gemm.cu) ----------------------------------------------------------------------------
+struct GemmArgs {
+  const __nv_bfloat16* a;  // [m_pad, lda]
+  const __nv_bfloat16* b;  // [n_pad, ldb]
+  void* d;                 // [m_store.., ldd] f32 or bf16
+  const float* bias;       // [n_pad] or nullptr
+  int m_pad, n_pad, k_pad;
+  long long lda, ldb, ldd;
+  int m_store, n_store;
+  int bn;        // N tile (multiple of 16, <= 256, divides n_pad)
+  int act;       // 0 none, 1 relu, 2 sigmoid
+  int out_bf16;  // 0 -> f32 output, 1 -> bf16 output
+  int num_sms;
+};
+cudaError_t launch_gemm_bf16(const GemmArgs& g, cudaStream_t stream);
+
+// ---- recurrent LSTM step (lstm.cu) ---------------------------------------------------------
+struct LstmStepArgs {
+  CUtensorMap tm_h;  // hidden-state slots  [(T+1)*b_pad rows, kh_pad], box {64, 128}
+  CUtensorMap tm_w;  // sliced W_hh         [4*out_pad rows,  kh_pad], box {64, 4*u}
+  const float* gx;   // [T*b_pad, 4*out_pad] sliced column order, bias folded in
+  float* c;          // [b_pad, out_pad] cell state
+  __nv_bfloat16* y;  // [(T+1)*b_pad, ldy] hidden-state slots (slot 0 = zeros)
+  float* raw;        // optional [b_pad, T, raw_ld] f32 copy of h (get_raw_features), or nullptr
+  float* pool_sum;   // optional [b_pad, out_pad] (last layer only)
+  float* pool_max;
+  float* pool_last;
+  const int* lengths;  // [b_pad]
+  int t, T;
+  int b_pad;   // 128 or 256
+  int u;       // hidden units per CTA (multiple of 4)
+  int n_cta;   // out_pad / u
+  int out_pad;
+  int kh_pad;  // multiple of 64
+  long long ldy;
+  long long raw_ld;
+};
+cudaError_t launch_lstm_step(const LstmStepArgs& a, cudaStream_t stream);
+
+// ---- small memory-bound kernels (misc.cu) --------------------------------------------------------
+// ids [B, T] int64 (batch-first, right padded) -> x0 [(T*b_pad), ldx] bf16, time-major rows t*b_pad + b
+cudaError_t launch_embed_gather(const int64_t* ids, int B, int T, int b_pad, const __nv_bfloat16* emb, int vocab,
+                                int e_pad, __nv_bfloat16* x0, long long ldx, int pad_idx, int* err_flag,
+                                cudaStream_t stream);
+// out[b] = [sum/len | max | last], b < B, first `e` units
+cudaError_t launch_pool_finalize(const float* pool_sum, const float* pool_max, const float* pool_last,
+                                 const int* lengths, int B, int e, int out_pad, float* out, cudaStream_t stream);
+// f32 [rows, cols] (row pitch ld_src) -> bf16 [rows_pad, ld_dst] with optional row permutation (src row of dst row r
+// = perm[r], or -1 for a zero row); columns >= cols zero filled.
+cudaError_t launch_convert_rows(const float* src, long long ld_src, int cols, const int* perm, int rows_dst,
+                                __nv_bfloat16* dst, long long ld_dst, cudaStream_t stream);
+cudaError_t launch_fill_f32(float* p, size_t n, float v, cudaStream_t stream);
+
+}  // namespace ie

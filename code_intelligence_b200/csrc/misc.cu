@@ -1,0 +1,143 @@
+// Memory-bound helper kernels of the encoder path (HBM-bound byte movement: coalesced 128-bit accesses, no
+// tensor cores) and the TMA descriptor factory.
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace ie {
+
+// ---------------------------------------------------------------------------------------------
+// TMA descriptors.  cuTensorMapEncodeTiled is fetched through the runtime so that the library has no link-time
+// dependency on libcuda (the build container has no driver).
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+cudaError_t make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t rows, uint64_t ld,
+                              uint32_t box_inner, uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) return cudaErrorNotSupported;
+  if (box_inner != 64 || box_rows == 0 || box_rows > 256 || (ld * 2) % 16 != 0 ||
+      (reinterpret_cast<uintptr_t>(base) & 15) != 0)
+    return cudaErrorInvalidValue;
+  cuuint64_t dims[2] = {inner, rows};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {box_inner, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// Embedding lookup (F.embedding inside fastai's EmbeddingDropout in eval mode; reference call site
+// Issue_Embeddings/flask_app/inference.py:57).  One warp per (t, b) row, 16-byte loads/stores.
+// Rows b >= B of the 128-padded batch get the pad token.
+// ---------------------------------------------------------------------------------------------
+__global__ void embed_gather_kernel(const int64_t* __restrict__ ids, int B, int T, int b_pad,
+                                    const uint4* __restrict__ emb, int vocab, int chunks /* e_pad*2/16 */,
+                                    uint4* __restrict__ x0, long long ldx_chunks, int pad_idx, int* err_flag) {
+  const int warps_per_block = blockDim.x >> 5;
+  const long long row = static_cast<long long>(blockIdx.x) * warps_per_block + (threadIdx.x >> 5);
+  const long long total = static_cast<long long>(T) * b_pad;
+  if (row >= total) return;
+  const int lane = threadIdx.x & 31;
+  const int t = static_cast<int>(row / b_pad);
+  const int b = static_cast<int>(row - static_cast<long long>(t) * b_pad);
+  long long id = pad_idx;
+  if (b < B) id = ids[static_cast<long long>(b) * T + t];
+  if (id < 0 || id >= vocab) {
+    if (lane == 0) atomicExch(err_flag, 1);
+    id = 0;
+  }
+  const uint4* src = emb + id * chunks;
+  uint4* dst = x0 + row * ldx_chunks;
+  for (int i = lane; i < chunks; i += 32) dst[i] = __ldg(src + i);
+}
+
+__global__ void pool_finalize_kernel(const float* __restrict__ pool_sum, const float* __restrict__ pool_max,
+                                     const float* __restrict__ pool_last, const int* __restrict__ lengths, int B, int e,
+                                     int out_pad, float* __restrict__ out) {
+  const int b = blockIdx.x;
+  if (b >= B) return;
+  const float inv = 1.0f / static_cast<float>(lengths[b]);
+  const long long po = static_cast<long long>(b) * out_pad;
+  float* o = out + static_cast<long long>(b) * 3 * e;
+  for (int i = threadIdx.x; i < e; i += blockDim.x) {
+    o[i] = pool_sum[po + i] * inv;
+    o[e + i] = pool_max[po + i];
+    o[2 * e + i] = pool_last[po + i];
+  }
+}
+
+__global__ void convert_rows_kernel(const float* __restrict__ src, long long ld_src, int cols, const int* __restrict__ perm,
+                                    int rows_dst, __nv_bfloat16* __restrict__ dst, long long ld_dst) {
+  const int r = blockIdx.x;
+  if (r >= rows_dst) return;
+  const int sr = perm ? perm[r] : r;
+  __nv_bfloat16* d = dst + static_cast<long long>(r) * ld_dst;
+  const float* s = src + static_cast<long long>(sr < 0 ? 0 : sr) * ld_src;
+  for (int c = threadIdx.x; c < ld_dst; c += blockDim.x) {
+    float v = 0.0f;
+    if (sr >= 0 && c < cols) v = s[c];
+    d[c] = __float2bfloat16_rn(v);
+  }
+}
+
+__global__ void fill_f32_kernel(float* p, size_t n, float v) {
+  size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (; i < n; i += stride) p[i] = v;
+}
+
+}  // namespace
+
+cudaError_t launch_embed_gather(const int64_t* ids, int B, int T, int b_pad, const __nv_bfloat16* emb, int vocab,
+                                int e_pad, __nv_bfloat16* x0, long long ldx, int pad_idx, int* err_flag,
+                                cudaStream_t stream) {
+  if (e_pad % 8 || ldx % 8) return cudaErrorInvalidValue;
+  const long long rows = static_cast<long long>(T) * b_pad;
+  const int wpb = 8;
+  const long long blocks = (rows + wpb - 1) / wpb;
+  embed_gather_kernel<<<static_cast<unsigned>(blocks), wpb * 32, 0, stream>>>(
+      ids, B, T, b_pad, reinterpret_cast<const uint4*>(emb), vocab, e_pad / 8, reinterpret_cast<uint4*>(x0), ldx / 8,
+      pad_idx, err_flag);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pool_finalize(const float* pool_sum, const float* pool_max, const float* pool_last,
+                                 const int* lengths, int B, int e, int out_pad, float* out, cudaStream_t stream) {
+  pool_finalize_kernel<<<B, 256, 0, stream>>>(pool_sum, pool_max, pool_last, lengths, B, e, out_pad, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_convert_rows(const float* src, long long ld_src, int cols, const int* perm, int rows_dst,
+                                __nv_bfloat16* dst, long long ld_dst, cudaStream_t stream) {
+  convert_rows_kernel<<<rows_dst, 256, 0, stream>>>(src, ld_src, cols, perm, rows_dst, dst, ld_dst);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_fill_f32(float* p, size_t n, float v, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  size_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  fill_f32_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(p, n, v);
+  return cudaGetLastError();
+}
+
+}  // namespace ie

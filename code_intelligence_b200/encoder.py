@@ -1,0 +1,181 @@
+"""IssueEncoder: thin Python owner of an `ie_encoder` handle (include/issue_emb_b200.h).
+
+Token ids -> 2400-d [mean | max | last] vectors, i.e. the arithmetic behind
+``InferenceWrapper._forward_pass`` + ``batch_seq_pool`` (Issue_Embeddings/flask_app/inference.py:55-57,
+215-246) executed by the sm_100a kernels in csrc/.  torch is used only for pinned host buffers, device tensors
+and streams.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import IE_FLAG_DEVICE_PTRS, IE_MAX_BATCH, check, ie_config
+
+
+def _layer_dims(n_layers, emb_sz, n_hid):
+    return [((emb_sz if l == 0 else n_hid), (n_hid if l != n_layers - 1 else emb_sz)) for l in range(n_layers)]
+
+
+def _f32c(a) -> np.ndarray:
+    if hasattr(a, "detach"):
+        a = a.detach().cpu().numpy()
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+class IssueEncoder:
+    """AWD-LSTM encoder of the reference's deployed shape by default
+    (Embedding(60000,800) -> LSTM 800->2400->2400->2400->800, notebooks/04_Inference.ipynb:157-187)."""
+
+    def __init__(self, n_layers: int = 4, emb_sz: int = 800, n_hid: int = 2400, vocab_sz: int = 60000,
+                 pad_idx: int = 1, device: int = 0):
+        self._lib = _lib.load()
+        self.n_layers, self.emb_sz, self.n_hid, self.vocab_sz, self.pad_idx, self.device = \
+            n_layers, emb_sz, n_hid, vocab_sz, pad_idx, device
+        self.out_dim = 3 * emb_sz
+        cfg = ie_config(n_layers, emb_sz, n_hid, vocab_sz, pad_idx, device, 0)
+        h = C.c_void_p()
+        check(self._lib.ie_encoder_create(C.byref(cfg), C.byref(h)))
+        self._h = h
+        self._pinned = {}
+
+    # ------------------------------------------------------------------ lifetime
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.ie_encoder_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ weights
+    def load_weights(self, emb, layers: Sequence[dict]) -> "IssueEncoder":
+        """emb [V,E]; layers[l] = dict(w_ih [4*out,in], w_hh [4*out,out], b_ih [4*out], b_hh [4*out]) in
+        torch.nn.LSTM layout (gate rows i|f|g|o)."""
+        emb = _f32c(emb)
+        if emb.shape != (self.vocab_sz, self.emb_sz):
+            raise ValueError(f"embedding shape {emb.shape} != {(self.vocab_sz, self.emb_sz)}")
+        if len(layers) != self.n_layers:
+            raise ValueError(f"expected {self.n_layers} layers, got {len(layers)}")
+        check(self._lib.ie_encoder_load_embedding(self._h, emb.ctypes.data))
+        for l, ((n_in, n_out), L) in enumerate(zip(_layer_dims(self.n_layers, self.emb_sz, self.n_hid), layers)):
+            w_ih, w_hh, b_ih, b_hh = (_f32c(L[k]) for k in ("w_ih", "w_hh", "b_ih", "b_hh"))
+            if w_ih.shape != (4 * n_out, n_in) or w_hh.shape != (4 * n_out, n_out) or b_ih.shape != (4 * n_out,) \
+                    or b_hh.shape != (4 * n_out,):
+                raise ValueError(f"layer {l}: bad weight shapes {w_ih.shape} {w_hh.shape} {b_ih.shape} {b_hh.shape}")
+            check(self._lib.ie_encoder_load_layer(self._h, l, w_ih.ctypes.data, w_hh.ctypes.data, b_ih.ctypes.data,
+                                                  b_hh.ctypes.data))
+        return self
+
+    def load_state_dict(self, sd: dict) -> "IssueEncoder":
+        """Accepts the fastai 1.0.53 AWD_LSTM encoder key layout (``save_encoder`` .pth / ``learn.model[0]``;
+        Issue_Embeddings/README.md:84-85): ``encoder.weight``, ``rnns.{l}.weight_hh_l0_raw`` (authoritative
+        W_hh in eval mode), ``rnns.{l}.module.weight_ih_l0``, ``rnns.{l}.module.bias_{ih,hh}_l0``.  Keys with a
+        leading ``0.`` (full SequentialRNN state dict) are accepted too."""
+        def get(*names):
+            for n in names:
+                for pre in ("", "0."):
+                    if pre + n in sd:
+                        return sd[pre + n]
+            raise KeyError(names[0])
+        layers = []
+        for l in range(self.n_layers):
+            layers.append(dict(
+                w_ih=get(f"rnns.{l}.module.weight_ih_l0", f"rnns.{l}.weight_ih_l0"),
+                w_hh=get(f"rnns.{l}.weight_hh_l0_raw", f"rnns.{l}.module.weight_hh_l0", f"rnns.{l}.weight_hh_l0"),
+                b_ih=get(f"rnns.{l}.module.bias_ih_l0", f"rnns.{l}.bias_ih_l0"),
+                b_hh=get(f"rnns.{l}.module.bias_hh_l0", f"rnns.{l}.bias_hh_l0")))
+        return self.load_weights(get("encoder.weight", "encoder_dp.emb.weight"), layers)
+
+    # ------------------------------------------------------------------ hot path
+    def encode_ids(self, ids, lengths=None) -> np.ndarray:
+        """ids (B,T) int64 right-padded with pad_idx, lengths (B,) -> (B, 3*emb_sz) float32 numpy.
+        B may exceed IE_MAX_BATCH; it is then processed in slices of IE_MAX_BATCH rows."""
+        ids = np.ascontiguousarray(np.asarray(ids.cpu() if hasattr(ids, "cpu") else ids), dtype=np.int64)
+        if ids.ndim != 2:
+            raise ValueError("ids must be (B, T)")
+        B, T = ids.shape
+        if lengths is None:
+            lengths = np.full(B, T, dtype=np.int32)
+        lengths = np.ascontiguousarray(np.asarray(lengths), dtype=np.int32)
+        assert lengths.shape[0] == B, 'Number of elements in lengths should match the first dimension of ids'
+        out = np.empty((B, self.out_dim), dtype=np.float32)
+        for b0 in range(0, B, IE_MAX_BATCH):
+            b1 = min(B, b0 + IE_MAX_BATCH)
+            sl = np.ascontiguousarray(ids[b0:b1])
+            ln = np.ascontiguousarray(lengths[b0:b1])
+            o = out[b0:b1]
+            check(self._lib.ie_encoder_encode(self._h, sl.ctypes.data, ln.ctypes.data, b1 - b0, T, o.ctypes.data, 0,
+                                              None))
+        return out
+
+    def encode_ids_device(self, ids, lengths, out=None, stream=None):
+        """Asynchronous device-resident variant: ids cuda int64 (B,T), lengths cuda int32 (B,), out cuda float32
+        (B, 3*emb_sz); B <= IE_MAX_BATCH.  Runs on `stream` (default: torch's current stream)."""
+        import torch
+        assert ids.is_cuda and lengths.is_cuda and ids.dtype == torch.int64 and lengths.dtype == torch.int32
+        ids, lengths = ids.contiguous(), lengths.contiguous()
+        B, T = ids.shape
+        if out is None:
+            out = torch.empty((B, self.out_dim), dtype=torch.float32, device=ids.device)
+        s = stream if stream is not None else torch.cuda.current_stream(ids.device)
+        check(self._lib.ie_encoder_encode(self._h, ids.data_ptr(), lengths.data_ptr(), B, T, out.data_ptr(),
+                                          IE_FLAG_DEVICE_PTRS, C.c_void_p(s.cuda_stream)))
+        return out
+
+    def raw_features(self, ids) -> np.ndarray:
+        """Last layer hidden states (B,T,emb_sz) float32 -- get_raw_features (inference.py:59-68)."""
+        ids = np.ascontiguousarray(np.asarray(ids.cpu() if hasattr(ids, "cpu") else ids), dtype=np.int64)
+        if ids.ndim != 2:
+            raise ValueError("ids must be (B, T)")
+        B, T = ids.shape
+        if B > IE_MAX_BATCH:
+            raise ValueError(f"B={B} > {IE_MAX_BATCH}")
+        raw = np.empty((B, T, self.emb_sz), dtype=np.float32)
+        check(self._lib.ie_encoder_raw_features(self._h, ids.ctypes.data, B, T, raw.ctypes.data, 0, None))
+        return raw
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.ie_encoder_launch_count(self._h))
+
+    # ------------------------------------------------------------------ bulk (df_to_embedding on token ids)
+    def encode_id_list(self, docs: List[np.ndarray], bs: int = 100, min_batches_rule: bool = True) -> np.ndarray:
+        """The bulk loop of ``df_to_embedding`` (py/code_intelligence/inference.py:171-229) from the
+        numericalised docs on: bs = min(bs, N//20+1), argsort by length, right-pad each batch to its own max
+        with pad_idx, encode, unsort with argsort(argsort); on RuntimeError (CUDA OOM) halve bs and retry.
+        Returns (N, 3*emb_sz) float32 in input order."""
+        n = len(docs)
+        if n == 0:
+            return np.empty((0, self.out_dim), dtype=np.float32)
+        if min_batches_rule:
+            bs = min(bs, (n // 20) + 1)
+        bs = max(1, min(bs, IE_MAX_BATCH))
+        length_arr = np.array([len(d) for d in docs])
+        if (length_arr < 1).any():
+            raise ValueError("empty token sequence")
+        len_mask = length_arr.argsort(kind="stable")
+        len_mask_reversed = len_mask.argsort()
+        ordered_lengths = length_arr[len_mask]
+        pooled = np.empty((n, self.out_dim), dtype=np.float32)
+        i = 0
+        while i < n:
+            try:
+                idx = len_mask[i:i + bs]
+                T = int(ordered_lengths[min(i + bs, n) - 1])
+                bp = np.full((len(idx), T), self.pad_idx, dtype=np.int64)
+                for r, j in enumerate(idx):
+                    bp[r, :length_arr[j]] = docs[j]
+                pooled[i:i + len(idx)] = self.encode_ids(bp, ordered_lengths[i:i + len(idx)])
+                i += bs
+            except RuntimeError as e:
+                if bs == 1:
+                    raise Exception(e)
+                bs = bs // 2
+        return pooled[len_mask_reversed, :]

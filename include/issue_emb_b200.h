@@ -1,0 +1,109 @@
+/* issue_emb_b200 -- C ABI of the B200-native Issue_Embeddings encoder hot path and the Label_Microservice
+ * MLP head (libissue_emb_b200.so).  Plain pointers and sizes only; no torch / C++ types.
+ *
+ * The reference (kubeflow/Code-Intelligence) has no FFI layer for this path: its "operator API" is the Python
+ * class InferenceWrapper and sklearn's MLPClassifier behind MLPWrapper.  Each entry point below states the
+ * reference interface it replaces (paths relative to the reference tree); INTEGRATION.md shows the ctypes
+ * binding a maintainer would add on the reference side.
+ *
+ * Conventions
+ *   - every function returns IE_OK (0) or a negative IE_ERR_* code and never aborts; ie_last_error() returns a
+ *     thread-local human-readable message for the last failing call on this thread.
+ *   - a handle owns its device weights and workspace; calls on one handle are serialised internally; handles may
+ *     be used from any host thread.
+ *   - `flags & IE_FLAG_DEVICE_PTRS`: ids / lengths / out (or X / probs) are device pointers on the handle's
+ *     device and the call is asynchronous on `stream`; otherwise they are host pointers (pinned or pageable)
+ *     and the call returns after the result has been copied back.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the handle's own stream).
+ */
+#ifndef ISSUE_EMB_B200_H_
+#define ISSUE_EMB_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IE_OK 0
+#define IE_ERR_INVALID (-1) /* bad argument / shape (Python shim raises ValueError)                        */
+#define IE_ERR_CUDA (-2)    /* CUDA runtime / launch failure (RuntimeError)                                  */
+#define IE_ERR_OOM (-3)     /* device memory exhausted (RuntimeError, so the reference's batch-halving loop   */
+                            /* py/code_intelligence/inference.py:214-223 keeps working)                       */
+#define IE_ERR_STATE (-4)   /* weights not loaded, wrong call order                                           */
+#define IE_ERR_TOKEN (-5)   /* a token id outside [0, vocab_sz) was seen (ValueError)                         */
+
+#define IE_FLAG_DEVICE_PTRS 1
+
+#define IE_MAX_BATCH 256 /* rows per ie_encoder_encode call (two 128-row UMMA tiles) */
+
+typedef struct ie_encoder ie_encoder;
+typedef struct ie_mlp ie_mlp;
+
+/* AWD-LSTM encoder shape.  Replaces what fastai's load_learner() unpickles at
+ * Issue_Embeddings/flask_app/inference.py:33-36 (model structure: notebooks/04_Inference.ipynb:157-187):
+ * Embedding(vocab_sz, emb_sz, padding_idx=pad_idx) -> n_layers x LSTM, in_0 = emb_sz, hidden = n_hid,
+ * out_{L-1} = emb_sz.  Output width is 3*emb_sz. */
+typedef struct ie_config {
+  int32_t n_layers; /* deployed reference model: 4 (north-star wording: 3) */
+  int32_t emb_sz;   /* 800  */
+  int32_t n_hid;    /* 2400 */
+  int32_t vocab_sz; /* 60000 */
+  int32_t pad_idx;  /* 1 (inference.py:36 learn.data.pad_idx) */
+  int32_t device;   /* CUDA device ordinal */
+  int32_t flags;    /* reserved, 0 */
+} ie_config;
+
+int ie_version(void);
+const char* ie_last_error(void);
+
+/* InferenceWrapper.__init__ (Issue_Embeddings/flask_app/inference.py:29-39): create the encoder ... */
+int ie_encoder_create(const ie_config* cfg, ie_encoder** out);
+void ie_encoder_destroy(ie_encoder* h);
+
+/* ... and load its weights (host pointers, f32, C-contiguous):
+ *   emb   [vocab_sz, emb_sz]                     state_dict key  encoder.weight
+ *   w_ih  [4*out_l, in_l]   rows i|f|g|o         rnns.{l}.module.weight_ih_l0
+ *   w_hh  [4*out_l, out_l]                       rnns.{l}.weight_hh_l0_raw
+ *   b_ih, b_hh [4*out_l]                         rnns.{l}.module.bias_{ih,hh}_l0
+ * (torch.nn.LSTM layout; key names per fastai 1.0.53 AWD_LSTM). */
+int ie_encoder_load_embedding(ie_encoder* h, const float* emb);
+int ie_encoder_load_layer(ie_encoder* h, int32_t layer, const float* w_ih, const float* w_hh, const float* b_ih,
+                          const float* b_hh);
+
+/* The hot path.  Replaces InferenceWrapper._forward_pass + batch_seq_pool
+ * (Issue_Embeddings/flask_app/inference.py:55-57 and :215-246; bulk loop py/code_intelligence/inference.py:207-212)
+ * and, with B == 1 and lengths[0] == T, get_pooled_features (inference.py:71-90):
+ *   ids     [B, T] int64, batch-first, right-padded with pad_idx (what pad_sequence builds, inference.py:201)
+ *   lengths [B] int32, 1 <= lengths[b] <= T
+ *   out     [B, 3*emb_sz] f32 = [mean | max | last] over the first lengths[b] steps of the last layer's hidden
+ *           states, zero initial state (encoder.reset(), inference.py:56)
+ * 1 <= B <= IE_MAX_BATCH. */
+int ie_encoder_encode(ie_encoder* h, const int64_t* ids, const int32_t* lengths, int32_t B, int32_t T, float* out,
+                      int32_t flags, void* stream);
+
+/* InferenceWrapper.get_raw_features (inference.py:59-68): the last layer's hidden states, raw [B, T, emb_sz] f32. */
+int ie_encoder_raw_features(ie_encoder* h, const int64_t* ids, int32_t B, int32_t T, float* raw, int32_t flags,
+                            void* stream);
+
+/* Number of kernels this handle has launched so far (bench.py reports it as gpu_launches). */
+int64_t ie_encoder_launch_count(const ie_encoder* h);
+
+/* MLP head.  Replaces sklearn MLPClassifier.predict_proba as called by MLPWrapper.predict_probabilities
+ * (py/label_microservice/mlp.py:56-63): relu hidden layers, logistic output (multilabel).
+ *   dims [n_layers + 1] = {D_in, hidden..., n_labels};  coef_l [dims[l], dims[l+1]] f32 (sklearn coefs_[l],
+ *   fan_in major), intercept_l [dims[l+1]].  X [n, D_in] f32 -> probs [n, n_labels] f32. */
+int ie_mlp_create(int32_t n_layers, const int32_t* dims, int32_t device, ie_mlp** out);
+int ie_mlp_load_layer(ie_mlp* m, int32_t layer, const float* coef, const float* intercept);
+int ie_mlp_predict_proba(ie_mlp* m, const float* X, int32_t n, float* probs, int32_t flags, void* stream);
+void ie_mlp_destroy(ie_mlp* m);
+
+/* Debug / test hook: D[M,N] = A[M,K] * B[N,K]^T (+bias) through the same tcgen05 GEMM the encoder uses.
+ * a [M,K], b [N,K], bias [N] or NULL: host f32 (rounded to bf16 on the device); d [M,N] host f32. */
+int ie_debug_gemm(const float* a, const float* b, const float* bias, int32_t M, int32_t N, int32_t K, int32_t act,
+                  float* d, int32_t device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ISSUE_EMB_B200_H_ */
