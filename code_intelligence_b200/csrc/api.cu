@@ -93,6 +93,10 @@ struct ie_encoder {
   size_t y_bytes_zeroed = 0;
   cudaStream_t own_stream = nullptr;
   int64_t launches = 0;
+  // phase boundary events of the last encode call: start, gather, (gemm_l, steps_l) x L, finalize
+  std::vector<cudaEvent_t> ev;
+  int ev_used = 0;
+  int last_T = 0, last_b_pad = 0;
   std::mutex mu;
 };
 
@@ -195,6 +199,16 @@ int ensure_workspace(ie_encoder* h, int b_pad, int T, bool want_raw) {
   return IE_OK;
 }
 
+int mark(ie_encoder* h, cudaStream_t s) {
+  if (h->ev_used >= static_cast<int>(h->ev.size())) {
+    cudaEvent_t e;
+    CK(cudaEventCreate(&e));
+    h->ev.push_back(e);
+  }
+  CK(cudaEventRecord(h->ev[h->ev_used++], s));
+  return IE_OK;
+}
+
 // the launch sequence shared by encode (pooled) and raw_features
 int run_encoder(ie_encoder* h, const int64_t* ids, const int32_t* lengths, int B, int T, float* out, float* raw_out,
                 int flags, cudaStream_t s) {
@@ -237,9 +251,14 @@ int run_encoder(ie_encoder* h, const int64_t* ids, const int32_t* lengths, int B
     ids_dev = h->ids.as<int64_t>();
   }
 
+  h->ev_used = 0;
+  h->last_T = T;
+  h->last_b_pad = b_pad;
+  if ((rc = mark(h, s)) != IE_OK) return rc;
   CK(ie::launch_embed_gather(ids_dev, B, T, b_pad, h->emb.as<__nv_bfloat16>(), c.vocab_sz, h->e_pad,
                              h->x0.as<__nv_bfloat16>(), h->e_pad, c.pad_idx, h->err.as<int>(), s));
   h->launches++;
+  if ((rc = mark(h, s)) != IE_OK) return rc;
 
   const long long rows = static_cast<long long>(T) * b_pad;
   int cur = 0;
@@ -268,6 +287,7 @@ int run_encoder(ie_encoder* h, const int64_t* ids, const int32_t* lengths, int B
     g.num_sms = h->num_sms;
     CK(ie::launch_gemm_bf16(g, s));
     h->launches++;
+    if ((rc = mark(h, s)) != IE_OK) return rc;
 
     // recurrence
     ie::LstmStepArgs a{};
@@ -295,6 +315,7 @@ int run_encoder(ie_encoder* h, const int64_t* ids, const int32_t* lengths, int B
       CK(ie::launch_lstm_step(a, s));
     }
     h->launches += T;
+    if ((rc = mark(h, s)) != IE_OK) return rc;
     layer_in = ybuf + static_cast<long long>(b_pad) * h->y_ld;  // slot 1 onwards
     layer_in_ld = h->y_ld;
     cur ^= 1;
@@ -306,6 +327,7 @@ int run_encoder(ie_encoder* h, const int64_t* ids, const int32_t* lengths, int B
     CK(ie::launch_pool_finalize(h->pool_sum.as<float>(), h->pool_max.as<float>(), h->pool_last.as<float>(),
                                 h->lengths.as<int>(), B, c.emb_sz, LL.out_pad, out_dev, s));
     h->launches++;
+    if ((rc = mark(h, s)) != IE_OK) return rc;
     if (!dev)
       CK(cudaMemcpyAsync(out, out_dev, static_cast<size_t>(B) * 3 * c.emb_sz * sizeof(float), cudaMemcpyDeviceToHost, s));
   }
@@ -370,6 +392,7 @@ void ie_encoder_destroy(ie_encoder* h) {
   DevBuf* bufs[] = {&h->emb, &h->ids, &h->lengths, &h->x0, &h->y[0], &h->y[1], &h->gx, &h->c, &h->pool_sum,
                     &h->pool_max, &h->pool_last, &h->out, &h->raw, &h->err};
   for (DevBuf* b : bufs) b->release();
+  for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
 }
@@ -412,7 +435,9 @@ int ie_encoder_encode(ie_encoder* h, const int64_t* ids, const int32_t* lengths,
   if (h == nullptr) return fail(IE_ERR_INVALID, "null handle");
   if (out == nullptr) return fail(IE_ERR_INVALID, "out is null");
   std::lock_guard<std::mutex> lk(h->mu);
-  cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : h->own_stream;
+  // device-pointer mode: `stream` is used verbatim (NULL = the legacy default stream, e.g. torch's default);
+  // host-pointer mode: NULL selects the handle's own stream
+  cudaStream_t s = (stream || (flags & IE_FLAG_DEVICE_PTRS)) ? static_cast<cudaStream_t>(stream) : h->own_stream;
   return run_encoder(h, ids, lengths, B, T, out, nullptr, flags, s);
 }
 
@@ -421,11 +446,22 @@ int ie_encoder_raw_features(ie_encoder* h, const int64_t* ids, int32_t B, int32_
   if (h == nullptr) return fail(IE_ERR_INVALID, "null handle");
   if (raw == nullptr) return fail(IE_ERR_INVALID, "raw is null");
   std::lock_guard<std::mutex> lk(h->mu);
-  cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : h->own_stream;
+  cudaStream_t s = (stream || (flags & IE_FLAG_DEVICE_PTRS)) ? static_cast<cudaStream_t>(stream) : h->own_stream;
   return run_encoder(h, ids, nullptr, B, T, nullptr, raw, flags, s);
 }
 
 int64_t ie_encoder_launch_count(const ie_encoder* h) { return h ? h->launches : 0; }
+
+int ie_encoder_last_phase_ms(ie_encoder* h, float* ms, int32_t cap) {
+  if (h == nullptr || ms == nullptr) return fail(IE_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (h->ev_used < 2) return fail(IE_ERR_STATE, "no encode call recorded");
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaEventSynchronize(h->ev[h->ev_used - 1]));
+  const int n = h->ev_used - 1;
+  for (int i = 0; i < n && i < cap; ++i) CK(cudaEventElapsedTime(&ms[i], h->ev[i], h->ev[i + 1]));
+  return n;
+}
 
 // ---------------------------------------------------------------------------------------------
 // MLP head
@@ -496,8 +532,8 @@ int ie_mlp_predict_proba(ie_mlp* m, const float* X, int32_t n, float* probs, int
     if (!L.loaded) return fail(IE_ERR_STATE, "MLP layer weights not loaded");
   std::lock_guard<std::mutex> lk(m->mu);
   CK(cudaSetDevice(m->device));
-  cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : m->own_stream;
   const bool dev = (flags & IE_FLAG_DEVICE_PTRS) != 0;
+  cudaStream_t s = (stream || dev) ? static_cast<cudaStream_t>(stream) : m->own_stream;
   const int nl = static_cast<int>(m->layers.size());
   const int d_in = m->dims[0], n_labels = m->dims[nl];
   const int chunk = 1 << 16;

@@ -145,37 +145,23 @@ class IssueEncoder:
     def launch_count(self) -> int:
         return int(self._lib.ie_encoder_launch_count(self._h))
 
+    def last_phase_ms(self) -> dict:
+        """CUDA-event device time of each phase of the last encode call (waits for it):
+        {'gather', 'gemm': [per layer], 'steps': [per layer], 'finalize'} in ms."""
+        buf = np.zeros(4 + 2 * self.n_layers, dtype=np.float32)
+        n = self._lib.ie_encoder_last_phase_ms(self._h, buf.ctypes.data, buf.size)
+        if n < 0:
+            check(n)
+        v = buf[:n].tolist()
+        return dict(gather=v[0], gemm=v[1:1 + 2 * self.n_layers:2], steps=v[2:2 + 2 * self.n_layers:2],
+                    finalize=v[1 + 2 * self.n_layers] if n > 1 + 2 * self.n_layers else 0.0)
+
     # ------------------------------------------------------------------ bulk (df_to_embedding on token ids)
     def encode_id_list(self, docs: List[np.ndarray], bs: int = 100, min_batches_rule: bool = True) -> np.ndarray:
         """The bulk loop of ``df_to_embedding`` (py/code_intelligence/inference.py:171-229) from the
         numericalised docs on: bs = min(bs, N//20+1), argsort by length, right-pad each batch to its own max
         with pad_idx, encode, unsort with argsort(argsort); on RuntimeError (CUDA OOM) halve bs and retry.
         Returns (N, 3*emb_sz) float32 in input order."""
-        n = len(docs)
-        if n == 0:
-            return np.empty((0, self.out_dim), dtype=np.float32)
-        if min_batches_rule:
-            bs = min(bs, (n // 20) + 1)
-        bs = max(1, min(bs, IE_MAX_BATCH))
-        length_arr = np.array([len(d) for d in docs])
-        if (length_arr < 1).any():
-            raise ValueError("empty token sequence")
-        len_mask = length_arr.argsort(kind="stable")
-        len_mask_reversed = len_mask.argsort()
-        ordered_lengths = length_arr[len_mask]
-        pooled = np.empty((n, self.out_dim), dtype=np.float32)
-        i = 0
-        while i < n:
-            try:
-                idx = len_mask[i:i + bs]
-                T = int(ordered_lengths[min(i + bs, n) - 1])
-                bp = np.full((len(idx), T), self.pad_idx, dtype=np.int64)
-                for r, j in enumerate(idx):
-                    bp[r, :length_arr[j]] = docs[j]
-                pooled[i:i + len(idx)] = self.encode_ids(bp, ordered_lengths[i:i + len(idx)])
-                i += bs
-            except RuntimeError as e:
-                if bs == 1:
-                    raise Exception(e)
-                bs = bs // 2
-        return pooled[len_mask_reversed, :]
+        from .bulk import encode_sorted_batches
+        return encode_sorted_batches(docs, self.encode_ids, self.pad_idx, self.out_dim, bs=bs, max_bs=IE_MAX_BATCH,
+                                     min_batches_rule=min_batches_rule)

@@ -1,0 +1,166 @@
+"""Label_Microservice MLP head on the B200.
+
+``MLPWrapper`` keeps the reference's interface (py/label_microservice/mlp.py:14-138) -- the constructor, ``fit``,
+``predict_probabilities``, ``find_probability_thresholds``, ``grid_search``, ``save_model`` / ``load_model`` -- but
+``predict_probabilities`` (mlp.py:56-63, sklearn ``MLPClassifier.predict_proba``) runs the fitted network's forward
+pass relu(relu(X W0 + b0) W1 + b1) ... -> sigmoid through the tcgen05 GEMM kernel behind ``ie_mlp_*``
+(include/issue_emb_b200.h).  Training-time methods stay on sklearn (out of scope).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import check
+
+
+class MLPHead:
+    """Owner of an ``ie_mlp`` handle: weights in sklearn layout (coefs_[l] is [fan_in, fan_out])."""
+
+    def __init__(self, coefs: Sequence[np.ndarray], intercepts: Sequence[np.ndarray], device: int = 0):
+        self._lib = _lib.load()
+        if len(coefs) != len(intercepts) or len(coefs) < 1:
+            raise ValueError("coefs / intercepts mismatch")
+        dims = [int(coefs[0].shape[0])] + [int(w.shape[1]) for w in coefs]
+        for l, (w, b) in enumerate(zip(coefs, intercepts)):
+            if w.shape != (dims[l], dims[l + 1]) or b.shape != (dims[l + 1],):
+                raise ValueError(f"layer {l}: coef {w.shape} intercept {b.shape} do not chain from {dims[l]}")
+        self.dims = dims
+        arr = (C.c_int32 * len(dims))(*dims)
+        h = C.c_void_p()
+        check(self._lib.ie_mlp_create(len(coefs), arr, device, C.byref(h)))
+        self._h = h
+        for l, (w, b) in enumerate(zip(coefs, intercepts)):
+            w = np.ascontiguousarray(w, dtype=np.float32)
+            b = np.ascontiguousarray(b, dtype=np.float32)
+            check(self._lib.ie_mlp_load_layer(self._h, l, w.ctypes.data, b.ctypes.data))
+
+    @classmethod
+    def from_sklearn(cls, clf, device: int = 0) -> "MLPHead":
+        est = getattr(clf, "best_estimator_", clf)  # GridSearchCV delegates (mlp.py:114)
+        if getattr(est, "out_activation_", "logistic") != "logistic" or getattr(est, "activation", "relu") != "relu":
+            raise ValueError("only relu hidden layers with a logistic (multilabel) output are supported")
+        return cls(est.coefs_, est.intercepts_, device)
+
+    def predict_proba(self, X) -> np.ndarray:
+        X = np.ascontiguousarray(np.asarray(X), dtype=np.float32)
+        if X.ndim != 2 or X.shape[1] != self.dims[0]:
+            raise ValueError(f"X must be (n, {self.dims[0]}), got {X.shape}")
+        probs = np.empty((X.shape[0], self.dims[-1]), dtype=np.float32)
+        if X.shape[0]:
+            check(self._lib.ie_mlp_predict_proba(self._h, X.ctypes.data, X.shape[0], probs.ctypes.data, 0, None))
+        return probs
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.ie_mlp_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class MLPWrapper:
+    """Wrapper for Multi-Layer Perceptron classifier (mirror of py/label_microservice/mlp.py:14)."""
+
+    def __init__(self, clf, model_file="model.dpkl", precision_threshold=0.7, recall_threshold=0.5,
+                 load_from_model=False, device: int = 0):
+        self._device = device
+        self._head: Optional[MLPHead] = None
+        if clf:
+            self.clf = clf
+        elif load_from_model:
+            self.load_model(model_file=model_file)
+        else:
+            raise Exception("You need to pass a MLPClassifier object to the wrapper")
+        self.model_file = model_file
+        self.precision_threshold = precision_threshold
+        self.recall_threshold = recall_threshold
+        self.precisions = None
+        self.probability_thresholds = None
+        self.recalls = None
+        self.total_labels_count = None
+
+    def fit(self, X, y):
+        """Train the classifier (sklearn on the CPU: training is out of scope of the B200 path)."""
+        self.clf.fit(X, y)
+        self._head = None
+
+    def predict_probabilities(self, X):
+        """Predict probabilities of all labels for data -> (n_samples, n_classes); on the B200."""
+        if self._head is None:
+            self._head = MLPHead.from_sklearn(self.clf, self._device)
+        return self._head.predict_proba(X)
+
+    def find_probability_thresholds(self, X, y, test_size=0.3):
+        """mlp.py:65-98: split, fit, then per label pick the threshold with the best precision among those meeting
+        both the precision and the recall threshold (None if there is none)."""
+        from sklearn.metrics import precision_recall_curve
+        from sklearn.model_selection import train_test_split
+        X_train, X_test, y_train, y_test = train_test_split(X, y, test_size=test_size, random_state=1234)
+        self.fit(X_train, y_train)
+        y_pred = self.predict_probabilities(X_test)
+        self.probability_thresholds, self.precisions, self.recalls = {}, {}, {}
+        self.total_labels_count = len(y_test[0])
+        for label in range(self.total_labels_count):
+            best_precision, best_recall, best_threshold = 0.0, 0.0, None
+            precision, recall, threshold = precision_recall_curve(np.array(y_test)[:, label], y_pred[:, label])
+            for prec, reca, thre in zip(precision[:-1], recall[:-1], threshold):
+                if prec >= self.precision_threshold and reca >= self.recall_threshold:
+                    if prec > best_precision:
+                        best_precision, best_recall, best_threshold = prec, reca, thre
+            self.probability_thresholds[label] = best_threshold
+            self.precisions[label] = best_precision
+            self.recalls[label] = best_recall
+
+    def grid_search(self, params=None, cv=5, n_jobs=-1):
+        from sklearn.model_selection import GridSearchCV
+        if not params:
+            params = {'hidden_layer_sizes': [(100,), (200,), (400,), (50, 50), (100, 100), (200, 200)],
+                      'alpha': [.001, .01, .1, 1, 10],
+                      'learning_rate': ['constant', 'adaptive'],
+                      'learning_rate_init': [.001, .01, .1]}
+        self.clf = GridSearchCV(self.clf, params, cv=cv, n_jobs=n_jobs)
+        self._head = None
+
+    def save_model(self, model_file=None):
+        import dill as dpickle
+        if model_file:
+            self.model_file = model_file
+        with open(self.model_file, 'wb') as f:
+            dpickle.dump(self.clf, f)
+
+    def load_model(self, model_file=None):
+        import dill as dpickle
+        if model_file:
+            self.model_file = model_file
+        if not os.path.exists(self.model_file):
+            raise Exception(f"Model path {self.model_file} does not exist")
+        with open(self.model_file, 'rb') as f:
+            self.clf = dpickle.load(f)
+        self._head = None
+
+
+def filter_predictions(label_names: Sequence[str], probabilities: Sequence[float],
+                       label_thresholds: Dict[str, Optional[float]]) -> Dict[str, float]:
+    """The end-to-end "labels" definition of RepoSpecificLabelModel.predict_issue_labels
+    (py/label_microservice/repo_specific_model.py:126-146): zip names with probabilities, drop a label when its
+    threshold is falsy (None / 0) or the probability is below it."""
+    predictions = dict(zip(label_names, probabilities))
+    labels_to_remove = []
+    for label, probability in predictions.items():
+        if not label_thresholds[label]:
+            labels_to_remove.append(label)
+            continue
+        if probability < label_thresholds[label]:
+            labels_to_remove.append(label)
+    for l in labels_to_remove:
+        del predictions[l]
+    return predictions

@@ -14,7 +14,8 @@
  *   - `flags & IE_FLAG_DEVICE_PTRS`: ids / lengths / out (or X / probs) are device pointers on the handle's
  *     device and the call is asynchronous on `stream`; otherwise they are host pointers (pinned or pageable)
  *     and the call returns after the result has been copied back.
- *   - `stream` is a cudaStream_t passed as void* (NULL = the handle's own stream).
+ *   - `stream` is a cudaStream_t passed as void*.  With host pointers NULL selects the handle's own stream; with
+ *     IE_FLAG_DEVICE_PTRS it is used verbatim (NULL = the legacy default stream, which is torch's default).
  */
 #ifndef ISSUE_EMB_B200_H_
 #define ISSUE_EMB_B200_H_
@@ -88,6 +89,11 @@ int ie_encoder_raw_features(ie_encoder* h, const int64_t* ids, int32_t B, int32_
 
 /* Number of kernels this handle has launched so far (bench.py reports it as gpu_launches). */
 int64_t ie_encoder_launch_count(const ie_encoder* h);
+
+/* Device time of each phase of the last encode call on this handle, from CUDA events recorded on the launching
+ * stream: ms[0] = embedding gather, then per layer l: ms[1+2l] = input-projection GEMM, ms[2+2l] = the T recurrent
+ * step launches, last = pool finalize.  Waits for the call to finish.  Returns the number of phases (or < 0). */
+int ie_encoder_last_phase_ms(ie_encoder* h, float* ms, int32_t cap);
 
 /* MLP head.  Replaces sklearn MLPClassifier.predict_proba as called by MLPWrapper.predict_probabilities
  * (py/label_microservice/mlp.py:56-63): relu hidden layers, logistic output (multilabel).

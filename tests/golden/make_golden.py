@@ -1,0 +1,83 @@
+"""Generates the committed golden fixtures in tests/golden/.  Run in the build container:
+
+    python tests/golden/make_golden.py
+
+* encoder_*.npz   -- outputs of the torch-module oracle (oracle/awd_lstm_ref.py; the modules fastai 1.0.53 wraps:
+                     the reference's own encoder is not importable here) on seeded inputs.
+                     Small configs carry their weights; the reference-shape (R4 / N3) fixtures carry only ids and
+                     expected outputs -- their weights are re-derived from the seed (torch CPU RNG is deterministic).
+* mlp_ref.npz     -- produced by IMPORTING THE REFERENCE: label_microservice.mlp.MLPWrapper from /root/reference/py
+                     (py/label_microservice/mlp.py:56-63) around a fitted sklearn MLPClassifier; stores coefs_,
+                     intercepts_, inputs and MLPWrapper.predict_probabilities outputs.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle import awd_lstm_ref as R  # noqa: E402
+
+
+def padded(docs, T, pad=1):
+    ids = np.full((len(docs), T), pad, dtype=np.int64)
+    for i, d in enumerate(docs):
+        ids[i, :len(d)] = d
+    return ids, np.array([len(d) for d in docs], dtype=np.int32)
+
+
+def encoder_fixture(name, n_layers, emb_sz, n_hid, vocab, B, T, min_len, seed, scale=1.0, with_weights=True):
+    torch.set_num_threads(os.cpu_count())
+    enc = R.make_encoder(seed, vocab, emb_sz, n_hid, n_layers, scale=scale)
+    docs = R.synthetic_ids(B, T, seed=seed + 1, vocab_sz=vocab, min_len=min_len)
+    ids, lengths = padded(docs, T)
+    out = R.encode_padded(enc, ids, lengths)
+    d = dict(cfg=np.array([n_layers, emb_sz, n_hid, vocab, seed], dtype=np.int64), scale=np.float64(scale), ids=ids,
+             lengths=lengths, expected=out.astype(np.float32))
+    if with_weights:
+        emb, layers = enc.export_weights()
+        d['emb'] = emb
+        for l, L in enumerate(layers):
+            for k, v in L.items():
+                d[f'l{l}_{k}'] = v
+    np.savez_compressed(os.path.join(HERE, name), **d)
+    print(name, out.shape, float(np.abs(out).mean()))
+
+
+def mlp_fixture():
+    sys.path.insert(0, '/root/reference/py')
+    from label_microservice.mlp import MLPWrapper  # the reference's own wrapper
+    from sklearn.neural_network import MLPClassifier
+    rng = np.random.default_rng(1234)
+    for tag, d_in, hidden, n_labels, n_train, n_test in [('small', 24, (32, 16), 5, 200, 64),
+                                                         ('prod', 1600, (600, 600), 40, 256, 96)]:
+        X = (rng.standard_normal((n_train, d_in)) * 0.1).astype(np.float32)
+        Y = (rng.random((n_train, n_labels)) < 0.2).astype(int)
+        Xt = (rng.standard_normal((n_test, d_in)) * 0.1).astype(np.float32)
+        clf = MLPClassifier(hidden_layer_sizes=hidden, random_state=1234, max_iter=8)
+        w = MLPWrapper(clf=clf)
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            w.fit(X, Y)
+        probs = w.predict_probabilities(Xt)
+        assert clf.out_activation_ == 'logistic'
+        d = dict(X=Xt, probs=np.asarray(probs, dtype=np.float64), n_layers=np.int64(len(clf.coefs_)))
+        for i, (W, b) in enumerate(zip(clf.coefs_, clf.intercepts_)):
+            d[f'coef{i}'] = np.asarray(W, dtype=np.float32)
+            d[f'intercept{i}'] = np.asarray(b, dtype=np.float32)
+        np.savez_compressed(os.path.join(HERE, f'mlp_ref_{tag}.npz'), **d)
+        print('mlp', tag, probs.shape, float(probs.mean()))
+
+
+if __name__ == '__main__':
+    encoder_fixture('encoder_tiny.npz', 2, 64, 128, 1000, 5, 9, 2, seed=11)
+    encoder_fixture('encoder_pad_dims.npz', 3, 50, 70, 300, 7, 12, 1, seed=12, scale=2.0)   # dims that need padding
+    encoder_fixture('encoder_r4.npz', 4, 800, 2400, 60000, 32, 128, None, seed=1234, with_weights=False)  # config 1
+    encoder_fixture('encoder_r4_varlen.npz', 4, 800, 2400, 60000, 24, 96, 5, seed=1234, scale=3.0, with_weights=False)
+    encoder_fixture('encoder_n3.npz', 3, 800, 2400, 60000, 16, 64, 8, seed=1234, with_weights=False)
+    mlp_fixture()

@@ -1,0 +1,130 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every symbol include/issue_emb_b200.h declares,
+it fails loudly without a GPU (no CPU fallback), the bulk driver reproduces the reference's sort / pad / unsort /
+OOM-halving logic, and the N>1 sharding + single all-gather works under gloo with world_size 2."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+from code_intelligence_b200 import _lib, bulk  # noqa: E402
+from oracle import awd_lstm_ref as R  # noqa: E402
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "issue_emb_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(ie_[a-z_0-9]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    lib = _lib.load()
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    assert declared == set(_lib.PROTOTYPES), (declared ^ set(_lib.PROTOTYPES))
+    assert lib.ie_version() >= 100
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback():
+    from code_intelligence_b200 import IssueEncoder
+    from code_intelligence_b200.mlp import MLPHead
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        IssueEncoder(2, 16, 32, 100)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        MLPHead([np.zeros((4, 3), np.float32)], [np.zeros(3, np.float32)])
+
+
+def test_product_code_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "code_intelligence_b200")
+    for dp, _, fns in os.walk(pkg):
+        for fn in fns:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dp, fn)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f"{fn} imports the oracle"
+                assert "/root/reference" not in src
+
+
+def _oracle_encoder_fn(enc):
+    return lambda ids, lengths: R.encode_padded(enc, ids, lengths)
+
+
+def test_bulk_loop_matches_reference_driver_restatement():
+    enc = R.make_encoder(3, 400, 24, 40, 3, scale=2.0)
+    docs = R.synthetic_ids(53, 30, seed=4, vocab_sz=400, min_len=1)
+    want = R.encode_bulk(enc, docs, bs=9)                       # restatement of df_to_embedding's loop
+    calls = []
+    def fn(ids, lengths):
+        calls.append(ids.shape)
+        return R.encode_padded(enc, ids, lengths)
+    got = bulk.encode_sorted_batches(docs, fn, pad_idx=1, out_dim=72, bs=9)
+    np.testing.assert_allclose(got, want, atol=1e-6)
+    assert got.dtype == np.float32 and got.shape == (53, 72)
+    assert calls[0][0] == min(9, 53 // 20 + 1)                  # bs rule: min(bs, N//20 + 1)
+    assert all(calls[i][1] <= calls[i + 1][1] for i in range(len(calls) - 1))   # sorted by length
+
+
+def test_bulk_loop_oom_halving_and_reraise():
+    enc = R.make_encoder(3, 400, 24, 40, 2)
+    docs = R.synthetic_ids(40, 12, seed=5, vocab_sz=400, min_len=2)
+    seen = []
+    def flaky(ids, lengths):
+        seen.append(ids.shape[0])
+        if ids.shape[0] > 2:
+            raise RuntimeError("CUDA out of memory (simulated)")
+        return R.encode_padded(enc, ids, lengths)
+    got = bulk.encode_sorted_batches(docs, flaky, 1, 72, bs=8, min_batches_rule=False)
+    np.testing.assert_allclose(got, R.encode_bulk(enc, docs, bs=100), atol=1e-6)
+    assert seen[:3] == [8, 4, 2]
+    def always(ids, lengths):
+        raise RuntimeError("CUDA out of memory (simulated)")
+    with pytest.raises(Exception):
+        bulk.encode_sorted_batches(docs, always, 1, 72, bs=4)
+    assert bulk.encode_sorted_batches([], always, 1, 72).shape == (0, 72)
+    with pytest.raises(ValueError):
+        bulk.encode_sorted_batches([np.array([], dtype=np.int64)], always, 1, 72)
+
+
+def test_shard_plan_round_robin():
+    lengths = np.array([5, 1, 9, 3, 7, 2, 8])
+    order, shards = bulk.shard_plan(lengths, 3)
+    assert sorted(np.concatenate(shards).tolist()) == list(range(7))
+    assert [lengths[s].tolist() for s in shards] == [[1, 5, 9], [2, 7], [3, 8]]
+
+
+_WORKER = r'''
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, {root!r})
+from code_intelligence_b200 import bulk
+from oracle import awd_lstm_ref as R
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
+enc = R.make_encoder(3, 400, 24, 40, 2)
+docs = R.synthetic_ids(37, 20, seed=6, vocab_sz=400, min_len=1)
+local = lambda d: bulk.encode_sorted_batches(d, lambda i, l: R.encode_padded(enc, i, l), 1, 72, bs=4, min_batches_rule=False)
+out = bulk.encode_bulk_distributed(docs, local)
+want = R.encode_bulk(enc, docs, bs=100)
+assert out.shape == (37, 72), out.shape
+assert np.allclose(out, want, atol=1e-6), np.abs(out - want).max()
+# an empty shard on one rank must still work
+one = bulk.encode_bulk_distributed(docs[:1], local)
+assert np.allclose(one, want[:1], atol=1e-6)
+dist.destroy_process_group()
+print("rank", sys.argv[1], "ok")
+'''
+
+
+def test_distributed_bulk_gloo_world2(tmp_path):
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    script = tmp_path / "w.py"
+    script.write_text(_WORKER.format(root=ROOT, port=port))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                              text=True) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
+        assert "ok" in o

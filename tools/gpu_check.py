@@ -29,7 +29,7 @@ def check_gemm():
     res = []
     for (M, N, K, act) in shapes:
         a = rng.standard_normal((M, K), dtype=np.float32)
-        b = rng.standard_normal((N, K), dtype=np.float32) / np.sqrt(K)
+        b = (rng.standard_normal((N, K), dtype=np.float32) / np.sqrt(K)).astype(np.float32)
         bias = rng.standard_normal(N, dtype=np.float32)
         d = np.zeros((M, N), dtype=np.float32)
         rc = lib.ie_debug_gemm(a.ctypes.data, b.ctypes.data, bias.ctypes.data, M, N, K, act, d.ctypes.data, 0)
