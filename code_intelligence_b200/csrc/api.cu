@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -74,6 +75,7 @@ struct Layer {
   int kin_pad = 0;          // padded K of the input projection
   int kh_pad = 0;           // padded K of the recurrent projection
   int bn = 0;               // GEMM N tile for the input projection
+  int cluster = 1;          // CTAs per cluster in the recurrent step (h tiles shared by TMA multicast)
   DevBuf w_ih, w_hh, bias;  // sliced layouts
   bool loaded = false;
 };
@@ -135,6 +137,12 @@ int plan_layers(ie_encoder* h) {
     L.kin_pad = prev_pad;
     L.kh_pad = static_cast<int>(round_up(L.out_pad, 64));
     prev_pad = L.kh_pad;
+    // cluster size for the h-tile multicast: largest of 8/4/2/1 dividing n_cta (IE_STEP_CLUSTER overrides)
+    int want = 4;
+    if (const char* e = getenv("IE_STEP_CLUSTER")) want = atoi(e);
+    L.cluster = 1;
+    for (int cs = 8; cs >= 1; cs >>= 1)
+      if (cs <= want && L.n_cta % cs == 0) { L.cluster = cs; break; }
     // largest multiple of 16 <= 256 dividing 4*out_pad
     const int n = 4 * L.out_pad;
     L.bn = 16;
@@ -294,6 +302,9 @@ int run_encoder(ie_encoder* h, const int64_t* ids, const int32_t* lengths, int B
     __nv_bfloat16* ybuf = h->y[cur].as<__nv_bfloat16>();
     CK(ie::make_tmap_bf16_2d(&a.tm_h, ybuf, L.kh_pad, static_cast<uint64_t>(rows + b_pad), h->y_ld, 64, 128));
     CK(ie::make_tmap_bf16_2d(&a.tm_w, L.w_hh.p, L.kh_pad, 4ull * L.out_pad, L.kh_pad, 64, 4 * L.u));
+    a.cluster = L.cluster;
+    CK(ie::make_tmap_bf16_2d(&a.tm_hs, ybuf, L.kh_pad, static_cast<uint64_t>(rows + b_pad), h->y_ld, 64,
+                             128 / L.cluster));
     a.gx = h->gx.as<float>();
     a.c = h->c.as<float>();
     a.y = ybuf;

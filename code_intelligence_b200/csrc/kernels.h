@@ -33,6 +33,7 @@ cudaError_t launch_gemm_bf16(const GemmArgs& g, cudaStream_t stream);
 // ---- recurrent LSTM step (lstm.cu) ---------------------------------------------------------
 struct LstmStepArgs {
   CUtensorMap tm_h;  // hidden-state slots  [(T+1)*b_pad rows, kh_pad], box {64, 128}
+  CUtensorMap tm_hs; // same tensor, box {64, 128/cluster}: the slice of a tile one CTA multicasts to its cluster
   CUtensorMap tm_w;  // sliced W_hh         [4*out_pad rows,  kh_pad], box {64, 4*u}
   const float* gx;   // [T*b_pad, 4*out_pad] sliced column order, bias folded in
   float* c;          // [b_pad, out_pad] cell state
@@ -46,6 +47,7 @@ struct LstmStepArgs {
   int b_pad;   // 128 or 256
   int u;       // hidden units per CTA (multiple of 4)
   int n_cta;   // out_pad / u
+  int cluster; // CTAs per cluster sharing the h tiles by TMA multicast (1, 2, 4 or 8; divides n_cta)
   int out_pad;
   int kh_pad;  // multiple of 64
   long long ldy;

@@ -31,8 +31,8 @@ constexpr int kStepStages = 4;
 
 template <int NCH>
 __global__ void __launch_bounds__(384, 1)
-lstm_step_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ CUtensorMap tm_w,
-                 const float* __restrict__ gx, float* __restrict__ cstate, __nv_bfloat16* __restrict__ y,
+lstm_step_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ CUtensorMap tm_hs,
+                 const __grid_constant__ CUtensorMap tm_w, const float* __restrict__ gx, float* __restrict__ cstate, __nv_bfloat16* __restrict__ y,
                  float* __restrict__ raw, float* __restrict__ pool_sum, float* __restrict__ pool_max,
                  float* __restrict__ pool_last, const int* __restrict__ lengths, int t, int T, int b_pad,
                  int out_pad, int num_k_blocks, long long ldy, long long raw_ld, int tmem_cols) {
@@ -55,22 +55,29 @@ lstm_step_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // Cluster of `csize` CTAs (different unit slices, same batch rows): every h_{t-1} tile is fetched from L2 once
+  // per cluster -- CTA r loads rows [r*128/csize, ...) of each tile and multicasts them to all CTAs of the cluster.
+  const uint32_t csize = cluster_nctarank();
+  const uint32_t crank = cluster_ctarank();
+  const uint16_t cmask = static_cast<uint16_t>((1u << csize) - 1u);
+  const uint32_t sub_rows = 128u / csize;
+  const uint32_t sub_bytes = sub_rows * 128u;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tm_h);
+    tma_prefetch_desc(csize > 1 ? &tm_hs : &tm_h);
     tma_prefetch_desc(&tm_w);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStepStages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], csize);  // one commit-arrive from every CTA that reads a stage we multicast into
     }
     mbar_init(tfull_bar, 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, tmem_cols);
   tc_fence_before();
-  __syncthreads();
+  if (csize > 1) cluster_sync(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -84,8 +91,14 @@ lstm_step_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant
         mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
         // weights first: they do not depend on the previous step
         tma_load_2d(sa + a_bytes, &tm_w, &full_bar[stage], kb * 64, blockIdx.x * N, kEvictLast);
-        for (int mt = 0; mt < m_tiles; ++mt)
-          tma_load_2d(sa + mt * a_tile_bytes, &tm_h, &full_bar[stage], kb * 64, t * b_pad + mt * 128, kEvictFirst);
+        if (csize == 1) {
+          for (int mt = 0; mt < m_tiles; ++mt)
+            tma_load_2d(sa + mt * a_tile_bytes, &tm_h, &full_bar[stage], kb * 64, t * b_pad + mt * 128, kEvictFirst);
+        } else {
+          for (int mt = 0; mt < m_tiles; ++mt)
+            tma_load_2d_mc(sa + mt * a_tile_bytes + crank * sub_bytes, &tm_hs, &full_bar[stage], kb * 64,
+                           t * b_pad + mt * 128 + static_cast<int>(crank * sub_rows), cmask, kEvictFirst);
+        }
         if (++stage == kStepStages) { stage = 0; phase ^= 1; }
       }
     }
@@ -104,7 +117,7 @@ lstm_step_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + mt * N, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
         }
-        umma_commit(&empty_bar[stage]);
+        if (csize == 1) umma_commit(&empty_bar[stage]); else umma_commit_mc(&empty_bar[stage], cmask);
         if (++stage == kStepStages) { stage = 0; phase ^= 1; }
       }
       umma_commit(tfull_bar);
@@ -183,7 +196,8 @@ lstm_step_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant
   }
 
   tc_fence_before();
-  __syncthreads();
+  // no CTA may exit while a peer can still multicast into its shared memory or arrive on its barriers
+  if (csize > 1) cluster_sync(); else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);
@@ -208,16 +222,28 @@ cudaError_t launch_step_t(const LstmStepArgs& a, cudaStream_t stream) {
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  kfn<<<a.n_cta, 128 + 128 * m_tiles, smem, stream>>>(a.tm_h, a.tm_w, a.gx, a.c, a.y, a.raw, a.pool_sum, a.pool_max,
-                                                       a.pool_last, a.lengths, a.t, a.T, a.b_pad, a.out_pad,
-                                                       a.kh_pad / 64, a.ldy, a.raw_ld, tmem_cols);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(a.n_cta);
+  cfg.blockDim = dim3(128 + 128 * m_tiles);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = a.cluster > 0 ? a.cluster : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kfn, a.tm_h, a.tm_hs, a.tm_w, a.gx, a.c, a.y, a.raw, a.pool_sum, a.pool_max,
+                            a.pool_last, a.lengths, a.t, a.T, a.b_pad, a.out_pad, a.kh_pad / 64, a.ldy, a.raw_ld,
+                            tmem_cols);
 }
 
 }  // namespace
 
 cudaError_t launch_lstm_step(const LstmStepArgs& a, cudaStream_t stream) {
   if (a.u % 4 || a.u < 4 || (a.b_pad != 128 && a.b_pad != 256) || a.kh_pad % 64) return cudaErrorInvalidValue;
+  if (a.cluster > 1 && (a.n_cta % a.cluster || 128 % a.cluster || a.cluster > 8)) return cudaErrorInvalidValue;
   switch (a.u / 4) {
     case 1: return launch_step_t<1>(a, stream);
     case 2: return launch_step_t<2>(a, stream);
