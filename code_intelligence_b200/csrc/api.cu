@@ -90,7 +90,9 @@ struct ie_encoder {
   DevBuf emb;  // bf16 [vocab, e_pad]
   bool emb_loaded = false;
   // workspace
-  DevBuf ids, lengths, x0, y[2], gx, c, pool_sum, pool_max, pool_last, out, raw, err;
+  DevBuf ids, lengths, x0, y[2], gx, c, pool_sum, pool_max, pool_last, out, raw, err, step_done;
+  int use_seq = 1;        // persistent per-layer kernel (lstm_seq.cu) when B_pad == 256 and the grid is co-resident
+  int seq_checked = 0;    // co-residency verified for every layer
   long long y_ld = 0;
   size_t y_bytes_zeroed = 0;
   cudaStream_t own_stream = nullptr;
@@ -204,6 +206,7 @@ int ensure_workspace(ie_encoder* h, int b_pad, int T, bool want_raw) {
   CK(h->pool_last.reserve(pb));
   CK(h->out.reserve(static_cast<size_t>(IE_MAX_BATCH) * 3 * c.emb_sz * sizeof(float)));
   if (want_raw) CK(h->raw.reserve(static_cast<size_t>(b_pad) * T * h->layers.back().out_pad * sizeof(float)));
+  CK(h->step_done.reserve(static_cast<size_t>(c.n_layers) * T * sizeof(unsigned)));
   return IE_OK;
 }
 
@@ -269,6 +272,19 @@ int run_encoder(ie_encoder* h, const int64_t* ids, const int32_t* lengths, int B
   if ((rc = mark(h, s)) != IE_OK) return rc;
 
   const long long rows = static_cast<long long>(T) * b_pad;
+  // persistent per-layer recurrent kernel: needs both 128-row halves and every CTA of a layer co-resident
+  bool seq = h->use_seq && b_pad == 256;
+  if (seq && !h->seq_checked) {
+    for (const Layer& L : h->layers) {
+      ie::LstmSeqArgs q{};
+      q.T = 1; q.b_pad = 256; q.u = L.u; q.n_cta = L.n_cta; q.out_pad = L.out_pad; q.kh_pad = L.kh_pad;
+      q.check_only = 1;
+      if (L.n_cta % 2 || ie::launch_lstm_seq(q, s) != cudaSuccess) { h->use_seq = 0; seq = false; }
+    }
+    cudaGetLastError();
+    h->seq_checked = 1;
+  }
+  if (seq) CK(cudaMemsetAsync(h->step_done.p, 0, static_cast<size_t>(c.n_layers) * T * sizeof(unsigned), s));
   int cur = 0;
   const __nv_bfloat16* layer_in = h->x0.as<__nv_bfloat16>();
   long long layer_in_ld = h->e_pad;
@@ -321,11 +337,22 @@ int run_encoder(ie_encoder* h, const int64_t* ids, const int32_t* lengths, int B
     a.kh_pad = L.kh_pad;
     a.ldy = h->y_ld;
     a.raw_ld = L.out_pad;
-    for (int t = 0; t < T; ++t) {
-      a.t = t;
-      CK(ie::launch_lstm_step(a, s));
+    if (seq) {
+      ie::LstmSeqArgs q{};
+      q.tm_h = a.tm_h; q.tm_w = a.tm_w; q.gx = a.gx; q.y = a.y; q.raw = a.raw;
+      q.pool_sum = a.pool_sum; q.pool_max = a.pool_max; q.pool_last = a.pool_last; q.lengths = a.lengths;
+      q.step_done = h->step_done.as<unsigned>() + static_cast<size_t>(l) * T;
+      q.T = T; q.b_pad = b_pad; q.u = L.u; q.n_cta = L.n_cta; q.out_pad = L.out_pad; q.kh_pad = L.kh_pad;
+      q.ldy = a.ldy; q.raw_ld = a.raw_ld; q.check_only = 0;
+      CK(ie::launch_lstm_seq(q, s));
+      h->launches += 1;
+    } else {
+      for (int t = 0; t < T; ++t) {
+        a.t = t;
+        CK(ie::launch_lstm_step(a, s));
+      }
+      h->launches += T;
     }
-    h->launches += T;
     if ((rc = mark(h, s)) != IE_OK) return rc;
     layer_in = ybuf + static_cast<long long>(b_pad) * h->y_ld;  // slot 1 onwards
     layer_in_ld = h->y_ld;
@@ -387,6 +414,7 @@ int ie_encoder_create(const ie_config* cfg, ie_encoder** out) {
   ie_encoder* h = new ie_encoder();
   h->cfg = *cfg;
   h->num_sms = sms;
+  if (const char* e = getenv("IE_SEQ")) h->use_seq = atoi(e);
   int rc = plan_layers(h);
   if (rc != IE_OK) { delete h; return rc; }
   e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);

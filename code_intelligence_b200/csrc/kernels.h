@@ -55,6 +55,24 @@ struct LstmStepArgs {
 };
 cudaError_t launch_lstm_step(const LstmStepArgs& a, cudaStream_t stream);
 
+// ---- persistent recurrent layer (lstm_seq.cu): all T steps in one launch, CTA pairs (cta_group::2) -------------
+struct LstmSeqArgs {
+  CUtensorMap tm_h;  // hidden-state slots  [(T+1)*256 rows, kh_pad], box {64, 128}
+  CUtensorMap tm_w;  // sliced W_hh         [4*out_pad rows, kh_pad], box {64, 4*u}
+  const float* gx;
+  __nv_bfloat16* y;
+  float* raw;
+  float* pool_sum;
+  float* pool_max;
+  float* pool_last;
+  const int* lengths;
+  unsigned* step_done;  // [T] zero-initialised grid-barrier counters
+  int T, b_pad, u, n_cta, out_pad, kh_pad;
+  long long ldy, raw_ld;
+  int check_only;  // 1: only check that the grid can be co-resident
+};
+cudaError_t launch_lstm_seq(const LstmSeqArgs& a, cudaStream_t stream);
+
 // ---- small memory-bound kernels (misc.cu) --------------------------------------------------------
 // ids [B, T] int64 (batch-first, right padded) -> x0 [(T*b_pad), ldx] bf16, time-major rows t*b_pad + b
 cudaError_t launch_embed_gather(const int64_t* ids, int B, int T, int b_pad, const __nv_bfloat16* emb, int vocab,

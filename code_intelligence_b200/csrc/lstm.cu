@@ -195,6 +195,7 @@ lstm_step_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant
     }
   }
 
+  __syncwarp();  // re-converge the single-lane role loops before the (aligned) barrier
   tc_fence_before();
   // no CTA may exit while a peer can still multicast into its shared memory or arrive on its barriers
   if (csize > 1) cluster_sync(); else __syncthreads();

@@ -1,0 +1,302 @@
+// Persistent recurrent kernel: ALL T timesteps of one LSTM layer in one launch (the same arithmetic as lstm.cu, which
+// stays as the fallback; reference call sites: Issue_Embeddings/flask_app/inference.py:56-57, :66-68, pooling :239).
+//
+// Why (profiles/README.md, round 1): the per-step kernel is bound by bytes delivered from L2 to the SMs
+// (196 MB per step ~ 12 TB/s chip wide) plus ~9 us of launch / prologue / epilogue that cannot overlap because step
+// t+1 needs every CTA's h_t.  This kernel
+//   * pairs CTAs (cluster of 2 on one TPC) into one M=256 tensor core (tcgen05 cta_group::2): CTA r of a pair
+//     holds batch rows [128r, 128r+128) and HALF of the pair's W_hh slice, so per step an SM ingests
+//     128 x K of h plus 2u x K of W instead of 256 x K plus 4u x K  (1.0 MB instead of 1.63 MB at H=2400);
+//   * keeps c_t in registers, barriers / TMEM / tensor maps alive across steps, and prefetches the next step's W_hh
+//     k-blocks (which do not depend on h_t) through their own ring while the epilogue and the grid barrier run;
+//   * replaces the kernel boundary by a grid-scope counter per step: epilogue threads store h_t, fence, and one
+//     thread per CTA does red.release; the h producer of every CTA spins (bounded) on ld.acquire, then
+//     fence.proxy.async, then issues the TMA loads of h_t.
+// All CTAs must be co-resident (grid <= SMs, 1 CTA/SM; checked with cudaOccupancyMaxActiveClusters by the caller).
+//
+// Warp roles per CTA (384 threads): 0 = h (A) producer, 1 = UMMA issuer (leader CTA only), 2 = TMEM allocator,
+// 3 = W producer, 4..11 = epilogue (two warps per TMEM lane quarter, each thread: one batch row x NCH chunks of 4 units).
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace ie {
+
+namespace {
+
+constexpr int kSeqThreads = 384;
+constexpr int kAStages = 6;  // 6 x 16 KB ring of h tiles
+
+template <int NCH>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSeqThreads, 1)
+lstm_seq_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ CUtensorMap tm_w,
+                const float* __restrict__ gx, __nv_bfloat16* __restrict__ y, float* __restrict__ raw,
+                float* __restrict__ pool_sum, float* __restrict__ pool_max, float* __restrict__ pool_last,
+                const int* __restrict__ lengths, unsigned* __restrict__ step_done, int T, int out_pad, int num_k_blocks,
+                long long ldy, long long raw_ld, int w_stages, int w_resident, int tmem_cols) {
+  constexpr int kBPad = 256;
+  constexpr int NH = NCH * 16;  // W rows this CTA contributes = accumulator columns of one slice
+  constexpr int N = 2 * NH;     // accumulator columns of the pair
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t rawaddr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (rawaddr & 1023u)) & 1023u);
+
+  constexpr uint32_t a_bytes = 128 * 64 * 2;
+  constexpr uint32_t w_bytes = NH * 64 * 2;
+  uint8_t* a_ring = smem;
+  uint8_t* w_ring = smem + kAStages * a_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(w_ring + static_cast<size_t>(w_stages) * w_bytes);
+  uint64_t* afull = bars;                     // [kAStages]  leader's copy is the live one
+  uint64_t* aempty = afull + kAStages;        // [kAStages]
+  uint64_t* wfull = aempty + kAStages;        // [w_stages]
+  uint64_t* wempty = wfull + w_stages;        // [w_stages]
+  uint64_t* tfull = wempty + w_stages;        // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_ctarank();  // 0 = leader
+  const int pair = blockIdx.x >> 1;
+  const unsigned total_ctas = gridDim.x;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_h);
+    tma_prefetch_desc(&tm_w);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kAStages; ++s) {
+      mbar_init(&afull[s], 2);   // leader's arrive.expect_tx + the peer's remote arrive
+      mbar_init(&aempty[s], 1);  // the leader's multicast commit
+    }
+    for (int s = 0; s < w_stages; ++s) {
+      mbar_init(&wfull[s], 2);
+      mbar_init(&wempty[s], 1);
+    }
+    mbar_init(tfull, 1);
+    fence_barrier_init();
+  }
+  cluster_sync();  // barrier inits visible to the peer before any remote arrive; both CTAs reach the 2-CTA alloc
+  if (warp == 2) tmem_alloc_pair(tmem_slot, tmem_cols);
+  tc_fence_before();
+  cluster_sync();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ---------------- h producer: this CTA's 128 batch rows of h_{t-1}, k-block by k-block ----------------------
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = 0; t < T; ++t) {
+        if (t > 0) {
+          wait_flag_ge(step_done + (t - 1), total_ctas);  // every CTA has published its slice of h_{t-1}
+          fence_proxy_async();                             // order the async-proxy (TMA) reads after the acquire
+        }
+        const int row0 = t * kBPad + static_cast<int>(crank) * 128;
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          mbar_wait(&aempty[stage], phase ^ 1);
+          if (crank == 0) mbar_arrive_expect_tx(&afull[stage], 2 * a_bytes);
+          else mbar_arrive_remote(&afull[stage], 0);
+          tma_load_2d_pair(a_ring + stage * a_bytes, &tm_h, &afull[stage], kb * 64, row0, kEvictNormal);
+          if (++stage == kAStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ---------------- W producer: this CTA's half of the pair's W_hh slice; free-running ahead of h -------------
+    if (lane == 0) {
+      const int wrow0 = blockIdx.x * NH;  // slices are laid out [cta][unit][gate]; CTA b owns rows [b*NH, +NH)
+      if (w_resident) {
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          if (crank == 0) mbar_arrive_expect_tx(&wfull[kb], 2 * w_bytes);
+          else mbar_arrive_remote(&wfull[kb], 0);
+          tma_load_2d_pair(w_ring + kb * w_bytes, &tm_w, &wfull[kb], kb * 64, wrow0, kEvictLast);
+        }
+      } else {
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int t = 0; t < T; ++t) {
+          for (int kb = 0; kb < num_k_blocks; ++kb) {
+            mbar_wait(&wempty[stage], phase ^ 1);
+            if (crank == 0) mbar_arrive_expect_tx(&wfull[stage], 2 * w_bytes);
+            else mbar_arrive_remote(&wfull[stage], 0);
+            tma_load_2d_pair(w_ring + stage * w_bytes, &tm_w, &wfull[stage], kb * 64, wrow0, kEvictLast);
+            if (++stage == w_stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- UMMA issuer (leader CTA): M = 256 (both CTAs' rows), N = 2*NH, K = 16 per instruction -----
+    if (crank == 0 && lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(256, N);
+      int as = 0, ws = 0;
+      uint32_t aph = 0, wph = 0;
+      for (int t = 0; t < T; ++t) {
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          mbar_wait(&afull[as], aph);
+          if (w_resident) {
+            if (t == 0) mbar_wait(&wfull[kb], 0);
+          } else {
+            mbar_wait(&wfull[ws], wph);
+          }
+          tc_fence_after();
+          const uint64_t da = umma_desc_sw128(smem_u32(a_ring + as * a_bytes));
+          const uint64_t db = umma_desc_sw128(smem_u32(w_ring + (w_resident ? kb : ws) * w_bytes));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16_pair(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          umma_commit_pair_mc(&aempty[as], 0x3);
+          if (++as == kAStages) { as = 0; aph ^= 1; }
+          if (!w_resident) {
+            umma_commit_pair_mc(&wempty[ws], 0x3);
+            if (++ws == w_stages) { ws = 0; wph ^= 1; }
+          }
+        }
+        umma_commit_pair_mc(tfull, 0x3);
+      }
+    }
+  } else if (warp >= 4) {
+    // ---------------- epilogue: gates, state update, h_t, pooling; then publish the step ----------------------
+    const int e = warp - 4;
+    const int q = e & 3;                      // TMEM lane quarter == warp % 4
+    const int half = e >> 2;                  // which NH columns of the pair's N this warp handles
+    const int row = static_cast<int>(crank) * 128 + q * 32 + lane;   // batch row
+    const int unit0 = pair * (2 * NCH * 4) + half * (NCH * 4);       // first hidden unit of this thread
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(half * NH);
+    const int len = (pool_sum != nullptr) ? lengths[row] : 1;
+    float cst[NCH * 4];
+#pragma unroll
+    for (int i = 0; i < NCH * 4; ++i) cst[i] = 0.0f;
+
+    for (int t = 0; t < T; ++t) {
+      const float4* gxp = reinterpret_cast<const float4*>(gx + (static_cast<long long>(t) * kBPad + row) * (4ll * out_pad) +
+                                                          4ll * unit0);
+      float4 gxr[NCH * 4];
+#pragma unroll
+      for (int i = 0; i < NCH * 4; ++i) gxr[i] = __ldg(gxp + i);
+
+      mbar_wait(tfull, static_cast<uint32_t>(t & 1));
+      tc_fence_after();
+      __nv_bfloat16* yrow = y + (static_cast<long long>(t + 1) * kBPad + row) * ldy + unit0;
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) {
+        uint32_t r[16];
+        __syncwarp();
+        tmem_ld16(taddr + ch * 16, r);
+        tmem_ld_wait();
+        float hn[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 gq = gxr[ch * 4 + j];
+          const float ig = sigmoid_acc(__uint_as_float(r[4 * j + 0]) + gq.x);
+          const float fg = sigmoid_acc(__uint_as_float(r[4 * j + 1]) + gq.y);
+          const float gg = tanh_acc(__uint_as_float(r[4 * j + 2]) + gq.z);
+          const float og = sigmoid_acc(__uint_as_float(r[4 * j + 3]) + gq.w);
+          const float cn = fg * cst[ch * 4 + j] + ig * gg;
+          cst[ch * 4 + j] = cn;
+          hn[j] = og * tanh_acc(cn);
+        }
+        *reinterpret_cast<uint2*>(yrow + ch * 4) = make_uint2(pack_bf16x2(hn[0], hn[1]), pack_bf16x2(hn[2], hn[3]));
+        if (raw != nullptr) {
+          float4* rp = reinterpret_cast<float4*>(raw + (static_cast<long long>(row) * T + t) * raw_ld + unit0 + ch * 4);
+          *rp = make_float4(hn[0], hn[1], hn[2], hn[3]);
+        }
+        if (pool_sum != nullptr && t < len) {
+          const long long po = static_cast<long long>(row) * out_pad + unit0 + ch * 4;
+          float4* ps = reinterpret_cast<float4*>(pool_sum + po);
+          float4* pm = reinterpret_cast<float4*>(pool_max + po);
+          float4 s, m;
+          if (t == 0) {
+            s = make_float4(hn[0], hn[1], hn[2], hn[3]);
+            m = s;
+          } else {
+            s = *ps;
+            m = *pm;
+            s.x += hn[0]; s.y += hn[1]; s.z += hn[2]; s.w += hn[3];
+            m.x = fmaxf(m.x, hn[0]); m.y = fmaxf(m.y, hn[1]); m.z = fmaxf(m.z, hn[2]); m.w = fmaxf(m.w, hn[3]);
+          }
+          *ps = s;
+          *pm = m;
+          if (t == len - 1) *reinterpret_cast<float4*>(pool_last + po) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+        }
+      }
+      // publish: TMEM reads are done (the next step's MMAs may overwrite the accumulator) and h_t is visible
+      tc_fence_before();
+      __threadfence();
+      named_bar_sync(1, 256);
+      if (threadIdx.x == 128) red_release_add(step_done + t, 1u);
+    }
+  }
+
+  __syncwarp();  // re-converge the single-lane role loops before the (aligned) cluster barrier
+  tc_fence_before();
+  cluster_sync();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, tmem_cols);
+  }
+}
+
+template <int NCH>
+cudaError_t launch_seq_t(const LstmSeqArgs& a, cudaStream_t stream) {
+  const int nh = NCH * 16;
+  const size_t a_ring = static_cast<size_t>(kAStages) * 128 * 64 * 2;
+  const size_t w_bytes = static_cast<size_t>(nh) * 64 * 2;
+  const int nkb = a.kh_pad / 64;
+  const size_t budget = 227 * 1024 - 1024 - a_ring - 2048;  // alignment slack + barriers
+  int w_stages = static_cast<int>(budget / w_bytes);
+  int resident = 0;
+  if (w_stages >= nkb) {
+    w_stages = nkb;
+    resident = 1;
+  }
+  if (w_stages > 40) w_stages = 40;
+  if (w_stages < 2) return cudaErrorInvalidValue;
+  const size_t smem = 1024 + a_ring + w_stages * w_bytes + (2 * kAStages + 2 * w_stages + 1) * 8 + 16;
+  int tmem_cols = 32;
+  while (tmem_cols < 2 * nh) tmem_cols <<= 1;
+  auto kfn = lstm_seq_kernel<NCH>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(a.n_cta);
+  cfg.blockDim = dim3(kSeqThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  if (a.check_only) {
+    // all CTAs must be co-resident: the step barrier would deadlock otherwise
+    int max_clusters = 0;
+    cfg.attrs = nullptr;  // the cluster shape is the kernel's compile-time __cluster_dims__(2,1,1)
+    cfg.numAttrs = 0;
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&max_clusters, kfn, &cfg);
+    if (e != cudaSuccess) return e;
+    return max_clusters * 2 >= a.n_cta ? cudaSuccess : cudaErrorCooperativeLaunchTooLarge;
+  }
+  kfn<<<a.n_cta, kSeqThreads, smem, stream>>>(a.tm_h, a.tm_w, a.gx, a.y, a.raw, a.pool_sum, a.pool_max, a.pool_last,
+                                               a.lengths, a.step_done, a.T, a.out_pad, nkb, a.ldy, a.raw_ld, w_stages,
+                                               resident, tmem_cols);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+// a.check_only != 0: only verify that the whole grid can be co-resident (no launch)
+cudaError_t launch_lstm_seq(const LstmSeqArgs& a, cudaStream_t stream) {
+  if (a.u % 4 || a.u < 4 || a.b_pad != 256 || a.kh_pad % 64 || a.n_cta % 2) return cudaErrorInvalidValue;
+  switch (a.u / 4) {
+    case 1: return launch_seq_t<1>(a, stream);
+    case 2: return launch_seq_t<2>(a, stream);
+    case 3: return launch_seq_t<3>(a, stream);
+    case 4: return launch_seq_t<4>(a, stream);
+    case 5: return launch_seq_t<5>(a, stream);
+    case 6: return launch_seq_t<6>(a, stream);
+    case 7: return launch_seq_t<7>(a, stream);
+    case 8: return launch_seq_t<8>(a, stream);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace ie
