@@ -91,6 +91,9 @@ struct ie_encoder {
   bool emb_loaded = false;
   // workspace
   DevBuf ids, lengths, x0, y[2], gx, c, pool_sum, pool_max, pool_last, out, raw, err, step_done;
+  DevBuf trace;           // debug timeline of one layer of the persistent kernel (ie_debug_seq_trace)
+  int trace_layer = -1;
+  int trace_T = 0, trace_ctas = 0;
   int use_seq = 1;        // persistent per-layer kernel (lstm_seq.cu) when B_pad == 256 and the grid is co-resident
   int seq_checked = 0;    // co-residency verified for every layer
   long long y_ld = 0;
@@ -344,6 +347,13 @@ int run_encoder(ie_encoder* h, const int64_t* ids, const int32_t* lengths, int B
       q.step_done = h->step_done.as<unsigned>() + static_cast<size_t>(l) * T;
       q.T = T; q.b_pad = b_pad; q.u = L.u; q.n_cta = L.n_cta; q.out_pad = L.out_pad; q.kh_pad = L.kh_pad;
       q.ldy = a.ldy; q.raw_ld = a.raw_ld; q.check_only = 0;
+      q.trace = nullptr;
+      if (l == h->trace_layer) {
+        CK(h->trace.reserve(static_cast<size_t>(L.n_cta) * T * 8 * sizeof(long long), true));
+        q.trace = h->trace.as<long long>();
+        h->trace_T = T;
+        h->trace_ctas = L.n_cta;
+      }
       CK(ie::launch_lstm_seq(q, s));
       h->launches += 1;
     } else {
@@ -429,7 +439,7 @@ void ie_encoder_destroy(ie_encoder* h) {
   cudaDeviceSynchronize();
   for (Layer& L : h->layers) { L.w_ih.release(); L.w_hh.release(); L.bias.release(); }
   DevBuf* bufs[] = {&h->emb, &h->ids, &h->lengths, &h->x0, &h->y[0], &h->y[1], &h->gx, &h->c, &h->pool_sum,
-                    &h->pool_max, &h->pool_last, &h->out, &h->raw, &h->err};
+                    &h->pool_max, &h->pool_last, &h->out, &h->raw, &h->err, &h->step_done, &h->trace};
   for (DevBuf* b : bufs) b->release();
   for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -490,6 +500,22 @@ int ie_encoder_raw_features(ie_encoder* h, const int64_t* ids, int32_t B, int32_
 }
 
 int64_t ie_encoder_launch_count(const ie_encoder* h) { return h ? h->launches : 0; }
+
+// debug: request a per-step timeline of `layer` in the persistent kernel on the next encode (layer < 0: off);
+// with out != NULL copy the last recorded timeline [n_cta][T][8] (SM clocks) and return n_cta*T
+int64_t ie_debug_seq_trace(ie_encoder* h, int32_t layer, long long* out, int64_t cap) {
+  if (h == nullptr) return fail(IE_ERR_INVALID, "null handle");
+  std::lock_guard<std::mutex> lk(h->mu);
+  h->trace_layer = layer;
+  if (out == nullptr) return 0;
+  const int64_t n = static_cast<int64_t>(h->trace_ctas) * h->trace_T;
+  if (n == 0 || n * 8 > cap) return fail(IE_ERR_STATE, "no trace recorded or buffer too small");
+  cudaSetDevice(h->cfg.device);
+  cudaDeviceSynchronize();
+  if (cudaMemcpy(out, h->trace.p, n * 8 * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess)
+    return fail(IE_ERR_CUDA, "trace copy failed");
+  return n;
+}
 
 int ie_encoder_last_phase_ms(ie_encoder* h, float* ms, int32_t cap) {
   if (h == nullptr || ms == nullptr) return fail(IE_ERR_INVALID, "null argument");

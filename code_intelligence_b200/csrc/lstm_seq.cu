@@ -32,7 +32,8 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
                 const float* __restrict__ gx, __nv_bfloat16* __restrict__ y, float* __restrict__ raw,
                 float* __restrict__ pool_sum, float* __restrict__ pool_max, float* __restrict__ pool_last,
                 const int* __restrict__ lengths, unsigned* __restrict__ step_done, int T, int out_pad, int num_k_blocks,
-                long long ldy, long long raw_ld, int w_stages, int w_resident, int tmem_cols) {
+                long long ldy, long long raw_ld, int w_stages, int w_resident, int tmem_cols,
+                long long* __restrict__ trace) {
   constexpr int kBPad = 256;
   constexpr int NH = NCH * 16;  // W rows this CTA contributes = accumulator columns of one slice
   constexpr int N = 2 * NH;     // accumulator columns of the pair
@@ -54,6 +55,8 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // optional per-CTA timeline (SM clock) of every step: [cta][t][8]; null in production
+#define IE_TRACE(slot, tt) do { if (trace) trace[(static_cast<long long>(blockIdx.x) * T + (tt)) * 8 + (slot)] = clock64(); } while (0)
   const uint32_t crank = cluster_ctarank();  // 0 = leader
   const int pair = blockIdx.x >> 1;
   const unsigned total_ctas = gridDim.x;
@@ -91,6 +94,7 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
           wait_flag_ge(step_done + (t - 1), total_ctas);  // every CTA has published its slice of h_{t-1}
           fence_proxy_async();                             // order the async-proxy (TMA) reads after the acquire
         }
+        IE_TRACE(0, t);
         const int row0 = t * kBPad + static_cast<int>(crank) * 128;
         for (int kb = 0; kb < num_k_blocks; ++kb) {
           mbar_wait(&aempty[stage], phase ^ 1);
@@ -99,6 +103,7 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
           tma_load_2d_pair(a_ring + stage * a_bytes, &tm_h, &afull[stage], kb * 64, row0, kEvictNormal);
           if (++stage == kAStages) { stage = 0; phase ^= 1; }
         }
+        IE_TRACE(1, t);
       }
     }
   } else if (warp == 3) {
@@ -134,6 +139,7 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
       for (int t = 0; t < T; ++t) {
         for (int kb = 0; kb < num_k_blocks; ++kb) {
           mbar_wait(&afull[as], aph);
+          if (kb == 0) IE_TRACE(2, t);
           if (w_resident) {
             if (t == 0) mbar_wait(&wfull[kb], 0);
           } else {
@@ -152,6 +158,7 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
           }
         }
         umma_commit_pair_mc(tfull, 0x3);
+        IE_TRACE(3, t);
       }
     }
   } else if (warp >= 4) {
@@ -173,9 +180,11 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
       float4 gxr[NCH * 4];
 #pragma unroll
       for (int i = 0; i < NCH * 4; ++i) gxr[i] = __ldg(gxp + i);
+      if (threadIdx.x == 128) IE_TRACE(7, t);
 
       mbar_wait(tfull, static_cast<uint32_t>(t & 1));
       tc_fence_after();
+      if (threadIdx.x == 128) IE_TRACE(4, t);
       __nv_bfloat16* yrow = y + (static_cast<long long>(t + 1) * kBPad + row) * ldy + unit0;
 #pragma unroll
       for (int ch = 0; ch < NCH; ++ch) {
@@ -220,10 +229,14 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
         }
       }
       // publish: TMEM reads are done (the next step's MMAs may overwrite the accumulator) and h_t is visible
+      if (threadIdx.x == 128) IE_TRACE(5, t);
       tc_fence_before();
       __threadfence();
       named_bar_sync(1, 256);
-      if (threadIdx.x == 128) red_release_add(step_done + t, 1u);
+      if (threadIdx.x == 128) {
+        IE_TRACE(6, t);
+        red_release_add(step_done + t, 1u);
+      }
     }
   }
 
@@ -277,7 +290,7 @@ cudaError_t launch_seq_t(const LstmSeqArgs& a, cudaStream_t stream) {
   }
   kfn<<<a.n_cta, kSeqThreads, smem, stream>>>(a.tm_h, a.tm_w, a.gx, a.y, a.raw, a.pool_sum, a.pool_max, a.pool_last,
                                                a.lengths, a.step_done, a.T, a.out_pad, nkb, a.ldy, a.raw_ld, w_stages,
-                                               resident, tmem_cols);
+                                               resident, tmem_cols, a.trace);
   return cudaGetLastError();
 }
 

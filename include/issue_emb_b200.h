@@ -95,6 +95,9 @@ int64_t ie_encoder_launch_count(const ie_encoder* h);
  * step launches, last = pool finalize.  Waits for the call to finish.  Returns the number of phases (or < 0). */
 int ie_encoder_last_phase_ms(ie_encoder* h, float* ms, int32_t cap);
 
+/* Debug hook: per-step timeline of one layer of the persistent recurrent kernel (tools/trace_seq.py). */
+int64_t ie_debug_seq_trace(ie_encoder* h, int32_t layer, long long* out, int64_t cap);
+
 /* MLP head.  Replaces sklearn MLPClassifier.predict_proba as called by MLPWrapper.predict_probabilities
  * (py/label_microservice/mlp.py:56-63): relu hidden layers, logistic output (multilabel).
  *   dims [n_layers + 1] = {D_in, hidden..., n_labels};  coef_l [dims[l], dims[l+1]] f32 (sklearn coefs_[l],
