@@ -94,6 +94,7 @@ struct ie_encoder {
   DevBuf trace;           // debug timeline of one layer of the persistent kernel (ie_debug_seq_trace)
   int trace_layer = -1;
   int trace_T = 0, trace_ctas = 0;
+  int fast_math = 0;      // IE_FAST_MATH / ie_config.flags bit 0: tanh.approx gates in the persistent kernel
   int use_seq = 1;        // persistent per-layer kernel (lstm_seq.cu) when B_pad == 256 and the grid is co-resident
   int seq_checked = 0;    // co-residency verified for every layer
   long long y_ld = 0;
@@ -347,6 +348,7 @@ int run_encoder(ie_encoder* h, const int64_t* ids, const int32_t* lengths, int B
       q.step_done = h->step_done.as<unsigned>() + static_cast<size_t>(l) * T;
       q.T = T; q.b_pad = b_pad; q.u = L.u; q.n_cta = L.n_cta; q.out_pad = L.out_pad; q.kh_pad = L.kh_pad;
       q.ldy = a.ldy; q.raw_ld = a.raw_ld; q.check_only = 0;
+      q.fast_math = h->fast_math;
       q.trace = nullptr;
       if (l == h->trace_layer) {
         CK(h->trace.reserve(static_cast<size_t>(L.n_cta) * T * 8 * sizeof(long long), true));
@@ -425,6 +427,8 @@ int ie_encoder_create(const ie_config* cfg, ie_encoder** out) {
   h->cfg = *cfg;
   h->num_sms = sms;
   if (const char* e = getenv("IE_SEQ")) h->use_seq = atoi(e);
+  h->fast_math = (cfg->flags & 1) ? 1 : 0;
+  if (const char* e = getenv("IE_FAST_MATH")) h->fast_math = atoi(e);
   int rc = plan_layers(h);
   if (rc != IE_OK) { delete h; return rc; }
   e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);

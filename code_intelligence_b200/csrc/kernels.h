@@ -70,6 +70,7 @@ struct LstmSeqArgs {
   int T, b_pad, u, n_cta, out_pad, kh_pad;
   long long ldy, raw_ld;
   int check_only;  // 1: only check that the grid can be co-resident
+  int fast_math;   // 1: single-MUFU tanh.approx gates
   long long* trace; // optional [n_cta][T][8] SM-clock timeline (debug), or nullptr
 };
 cudaError_t launch_lstm_seq(const LstmSeqArgs& a, cudaStream_t stream);

@@ -24,7 +24,7 @@ namespace ie {
 namespace {
 
 constexpr int kSeqThreads = 384;
-constexpr int kAStages = 6;  // 6 x 16 KB ring of h tiles
+constexpr int kAStages = 8;  // 8 x 16 KB ring of h tiles (the stream is latency bound: bytes in flight matter)
 
 template <int NCH>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSeqThreads, 1)
@@ -32,7 +32,7 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
                 const float* __restrict__ gx, __nv_bfloat16* __restrict__ y, float* __restrict__ raw,
                 float* __restrict__ pool_sum, float* __restrict__ pool_max, float* __restrict__ pool_last,
                 const int* __restrict__ lengths, unsigned* __restrict__ step_done, int T, int out_pad, int num_k_blocks,
-                long long ldy, long long raw_ld, int w_stages, int w_resident, int tmem_cols,
+                long long ldy, long long raw_ld, int w_stages, int w_resident, int tmem_cols, int fast_math,
                 long long* __restrict__ trace) {
   constexpr int kBPad = 256;
   constexpr int NH = NCH * 16;  // W rows this CTA contributes = accumulator columns of one slice
@@ -91,7 +91,7 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
       uint32_t phase = 0;
       for (int t = 0; t < T; ++t) {
         if (t > 0) {
-          wait_flag_ge(step_done + (t - 1), total_ctas);  // every CTA has published its slice of h_{t-1}
+          wait_flag_ge_relaxed(step_done + (t - 1), total_ctas);  // every CTA has published its slice of h_{t-1}
           fence_proxy_async();                             // order the async-proxy (TMA) reads after the acquire
         }
         IE_TRACE(0, t);
@@ -181,6 +181,13 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
 #pragma unroll
       for (int i = 0; i < NCH * 4; ++i) gxr[i] = __ldg(gxp + i);
       if (threadIdx.x == 128) IE_TRACE(7, t);
+      if (t + 1 < T) {
+        // pull the next step's Gx rows from HBM into L2 while this step streams, so that the loads at the top of
+        // step t+1 are short and do not queue in front of the step barrier traffic
+        const char* nx = reinterpret_cast<const char*>(gxp) + static_cast<long long>(kBPad) * out_pad * 16ll;
+#pragma unroll
+        for (int i = 0; i < (NCH * 64 + 127) / 128 + 1; ++i) prefetch_l2(nx + i * 128);
+      }
 
       mbar_wait(tfull, static_cast<uint32_t>(t & 1));
       tc_fence_after();
@@ -196,13 +203,19 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float4 gq = gxr[ch * 4 + j];
-          const float ig = sigmoid_acc(__uint_as_float(r[4 * j + 0]) + gq.x);
-          const float fg = sigmoid_acc(__uint_as_float(r[4 * j + 1]) + gq.y);
-          const float gg = tanh_acc(__uint_as_float(r[4 * j + 2]) + gq.z);
-          const float og = sigmoid_acc(__uint_as_float(r[4 * j + 3]) + gq.w);
-          const float cn = fg * cst[ch * 4 + j] + ig * gg;
+          const float zi = __uint_as_float(r[4 * j + 0]) + gq.x;
+          const float zf = __uint_as_float(r[4 * j + 1]) + gq.y;
+          const float zg = __uint_as_float(r[4 * j + 2]) + gq.z;
+          const float zo = __uint_as_float(r[4 * j + 3]) + gq.w;
+          float cn;
+          if (fast_math) {
+            cn = sigmoid_fast(zf) * cst[ch * 4 + j] + sigmoid_fast(zi) * tanh_fast(zg);
+            hn[j] = sigmoid_fast(zo) * tanh_fast(cn);
+          } else {
+            cn = sigmoid_acc(zf) * cst[ch * 4 + j] + sigmoid_acc(zi) * tanh_acc(zg);
+            hn[j] = sigmoid_acc(zo) * tanh_acc(cn);
+          }
           cst[ch * 4 + j] = cn;
-          hn[j] = og * tanh_acc(cn);
         }
         *reinterpret_cast<uint2*>(yrow + ch * 4) = make_uint2(pack_bf16x2(hn[0], hn[1]), pack_bf16x2(hn[2], hn[3]));
         if (raw != nullptr) {
@@ -231,11 +244,11 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
       // publish: TMEM reads are done (the next step's MMAs may overwrite the accumulator) and h_t is visible
       if (threadIdx.x == 128) IE_TRACE(5, t);
       tc_fence_before();
-      __threadfence();
       named_bar_sync(1, 256);
       if (threadIdx.x == 128) {
+        __threadfence();  // cumulative: covers the h stores of all 256 epilogue threads ordered by the barrier
+        red_relaxed_add(step_done + t, 1u);
         IE_TRACE(6, t);
-        red_release_add(step_done + t, 1u);
       }
     }
   }
@@ -290,7 +303,7 @@ cudaError_t launch_seq_t(const LstmSeqArgs& a, cudaStream_t stream) {
   }
   kfn<<<a.n_cta, kSeqThreads, smem, stream>>>(a.tm_h, a.tm_w, a.gx, a.y, a.raw, a.pool_sum, a.pool_max, a.pool_last,
                                                a.lengths, a.step_done, a.T, a.out_pad, nkb, a.ldy, a.raw_ld, w_stages,
-                                               resident, tmem_cols, a.trace);
+                                               resident, tmem_cols, a.fast_math, a.trace);
   return cudaGetLastError();
 }
 

@@ -286,4 +286,34 @@ __device__ __forceinline__ float sigmoid_acc(float x) { return __fdividef(1.0f, 
 // tanh(x) = 1 - 2/(exp(2x)+1): abs error ~1e-7, saturates correctly for |x| large
 __device__ __forceinline__ float tanh_acc(float x) { return 1.0f - __fdividef(2.0f, __expf(2.0f * x) + 1.0f); }
 
+// single-MUFU variants (tanh.approx.f32, max relative error 2^-11): the epilogue of the recurrent kernels is bound by
+// the 16/clk/SM special-function unit (10 MUFU per cell with the accurate forms, 5 with these)
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ unsigned ld_relaxed(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// bounded spin with relaxed loads, one acquire fence at the end
+__device__ __forceinline__ void wait_flag_ge_relaxed(const unsigned* p, unsigned target) {
+  if (ld_relaxed(p) < target) {
+    const long long t0 = clock64();
+    uint32_t spins = 0;
+    while (ld_relaxed(p) < target) {
+      if (((++spins) & 0xFFu) == 0 && (clock64() - t0) > 4000000000ll) __trap();
+    }
+  }
+  __threadfence();
+}
+__device__ __forceinline__ void red_relaxed_add(unsigned* p, unsigned v) {
+  asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 }  // namespace ie

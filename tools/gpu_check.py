@@ -94,6 +94,12 @@ def check_n3():
     return [_enc_parity(3, 800, 2400, 60000, 32, 64, min_len=16, scale=3.0)]
 
 
+def check_n3b():
+    # B=256 so that the persistent kernel path is exercised with "trained-like" weights, T=96
+    return [_enc_parity(3, 800, 2400, 60000, 256, 96, min_len=16, scale=3.0),
+            _enc_parity(4, 800, 2400, 60000, 256, 96, min_len=16, scale=1.0)]
+
+
 def check_speed():
     """B=256, T=512 R4 with device-resident inputs: per-encode CUDA-event time."""
     import numpy as np
@@ -125,7 +131,7 @@ def check_speed():
     return out
 
 
-CHECKS = dict(gemm=check_gemm, tiny=check_tiny, r4_small=check_r4_small, n3=check_n3, speed=check_speed)
+CHECKS = dict(gemm=check_gemm, tiny=check_tiny, r4_small=check_r4_small, n3=check_n3, n3b=check_n3b, speed=check_speed)
 
 if __name__ == '__main__':
     ap = argparse.ArgumentParser()
