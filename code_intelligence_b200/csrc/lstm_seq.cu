@@ -24,7 +24,12 @@ namespace ie {
 namespace {
 
 constexpr int kSeqThreads = 384;
-constexpr int kAStages = 8;  // 8 x 16 KB ring of h tiles (the stream is latency bound: bytes in flight matter)
+// The single UMMA-issuing thread is the bottleneck of the stream (measured: ~90 cycles per mbarrier wait, ~50 per commit,
+// ~45 per MMA issue against 80 cycles of tensor time per M=256,N=160,K=16 MMA), so barriers guard GROUPS of 64-wide
+// k-blocks: one wait / commit per kGA (h) or kGW (W_hh) k-blocks.
+constexpr int kGA = 2;       // k-blocks per h stage (32 KB)
+constexpr int kAStages = 4;  // 4 x 32 KB ring of h tiles
+constexpr int kGW = 4;       // k-blocks per W_hh stage (ring mode)
 
 template <int NCH>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSeqThreads, 1)
@@ -44,8 +49,10 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
   constexpr uint32_t a_bytes = 128 * 64 * 2;
   constexpr uint32_t w_bytes = NH * 64 * 2;
   uint8_t* a_ring = smem;
-  uint8_t* w_ring = smem + kAStages * a_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(w_ring + static_cast<size_t>(w_stages) * w_bytes);
+  uint8_t* w_ring = smem + kAStages * kGA * a_bytes;
+  // ring mode: w_stages stages of kGW k-blocks; resident mode: w_stages == num_k_blocks single k-block slots
+  const uint32_t w_stage_bytes = w_resident ? w_bytes : kGW * w_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(w_ring + static_cast<size_t>(w_stages) * w_stage_bytes);
   uint64_t* afull = bars;                     // [kAStages]  leader's copy is the live one
   uint64_t* aempty = afull + kAStages;        // [kAStages]
   uint64_t* wfull = aempty + kAStages;        // [w_stages]
@@ -55,8 +62,9 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  // optional per-CTA timeline (SM clock) of every step: [cta][t][8]; null in production
-#define IE_TRACE(slot, tt) do { if (trace) trace[(static_cast<long long>(blockIdx.x) * T + (tt)) * 8 + (slot)] = clock64(); } while (0)
+  // optional per-CTA timeline (%globaltimer, ns) of every step: [cta][t][8]; null in production
+#define IE_TRACE(slot, tt) do { if (trace) { unsigned long long _g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_g)); \
+    trace[(static_cast<long long>(blockIdx.x) * T + (tt)) * 8 + (slot)] = static_cast<long long>(_g); } } while (0)
   const uint32_t crank = cluster_ctarank();  // 0 = leader
   const int pair = blockIdx.x >> 1;
   const unsigned total_ctas = gridDim.x;
@@ -96,11 +104,14 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
         }
         IE_TRACE(0, t);
         const int row0 = t * kBPad + static_cast<int>(crank) * 128;
-        for (int kb = 0; kb < num_k_blocks; ++kb) {
+        for (int kb0 = 0; kb0 < num_k_blocks; kb0 += kGA) {
+          const int n = min(kGA, num_k_blocks - kb0);
           mbar_wait(&aempty[stage], phase ^ 1);
-          if (crank == 0) mbar_arrive_expect_tx(&afull[stage], 2 * a_bytes);
+          if (crank == 0) mbar_arrive_expect_tx(&afull[stage], 2 * n * a_bytes);
           else mbar_arrive_remote(&afull[stage], 0);
-          tma_load_2d_pair(a_ring + stage * a_bytes, &tm_h, &afull[stage], kb * 64, row0, kEvictNormal);
+          for (int j = 0; j < n; ++j)
+            tma_load_2d_pair(a_ring + (stage * kGA + j) * a_bytes, &tm_h, &afull[stage], (kb0 + j) * 64, row0,
+                             kEvictNormal);
           if (++stage == kAStages) { stage = 0; phase ^= 1; }
         }
         IE_TRACE(1, t);
@@ -120,11 +131,14 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
         int stage = 0;
         uint32_t phase = 0;
         for (int t = 0; t < T; ++t) {
-          for (int kb = 0; kb < num_k_blocks; ++kb) {
+          for (int kb0 = 0; kb0 < num_k_blocks; kb0 += kGW) {
+            const int n = min(kGW, num_k_blocks - kb0);
             mbar_wait(&wempty[stage], phase ^ 1);
-            if (crank == 0) mbar_arrive_expect_tx(&wfull[stage], 2 * w_bytes);
+            if (crank == 0) mbar_arrive_expect_tx(&wfull[stage], 2 * n * w_bytes);
             else mbar_arrive_remote(&wfull[stage], 0);
-            tma_load_2d_pair(w_ring + stage * w_bytes, &tm_w, &wfull[stage], kb * 64, wrow0, kEvictLast);
+            for (int j = 0; j < n; ++j)
+              tma_load_2d_pair(w_ring + (stage * kGW + j) * w_bytes, &tm_w, &wfull[stage], (kb0 + j) * 64, wrow0,
+                               kEvictLast);
             if (++stage == w_stages) { stage = 0; phase ^= 1; }
           }
         }
@@ -134,25 +148,34 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
     // ---------------- UMMA issuer (leader CTA): M = 256 (both CTAs' rows), N = 2*NH, K = 16 per instruction -----
     if (crank == 0 && lane == 0) {
       const uint32_t idesc = umma_idesc_bf16(256, N);
+      const uint32_t a_base = smem_u32(a_ring);
+      const uint32_t w_base = smem_u32(w_ring);
       int as = 0, ws = 0;
       uint32_t aph = 0, wph = 0;
       for (int t = 0; t < T; ++t) {
         for (int kb = 0; kb < num_k_blocks; ++kb) {
-          mbar_wait(&afull[as], aph);
-          if (kb == 0) IE_TRACE(2, t);
+          const int ja = kb % kGA;   // position inside the current h stage
+          const int jw = kb % kGW;   // position inside the current W stage (ring mode)
+          if (ja == 0) {
+            mbar_wait(&afull[as], aph);
+            if (kb == 0) IE_TRACE(2, t);
+          }
           if (w_resident) {
             if (t == 0) mbar_wait(&wfull[kb], 0);
-          } else {
+          } else if (jw == 0) {
             mbar_wait(&wfull[ws], wph);
           }
           tc_fence_after();
-          const uint64_t da = umma_desc_sw128(smem_u32(a_ring + as * a_bytes));
-          const uint64_t db = umma_desc_sw128(smem_u32(w_ring + (w_resident ? kb : ws) * w_bytes));
+          const uint64_t da = umma_desc_sw128(a_base + (as * kGA + ja) * a_bytes);
+          const uint64_t db = umma_desc_sw128(w_base + (w_resident ? kb : ws * kGW + jw) * w_bytes);
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_bf16_pair(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-          umma_commit_pair_mc(&aempty[as], 0x3);
-          if (++as == kAStages) { as = 0; aph ^= 1; }
-          if (!w_resident) {
+          const bool last = (kb == num_k_blocks - 1);
+          if (ja == kGA - 1 || last) {
+            umma_commit_pair_mc(&aempty[as], 0x3);
+            if (++as == kAStages) { as = 0; aph ^= 1; }
+          }
+          if (!w_resident && (jw == kGW - 1 || last)) {
             umma_commit_pair_mc(&wempty[ws], 0x3);
             if (++ws == w_stages) { ws = 0; wph ^= 1; }
           }
@@ -265,19 +288,22 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
 template <int NCH>
 cudaError_t launch_seq_t(const LstmSeqArgs& a, cudaStream_t stream) {
   const int nh = NCH * 16;
-  const size_t a_ring = static_cast<size_t>(kAStages) * 128 * 64 * 2;
+  const size_t a_ring = static_cast<size_t>(kAStages) * kGA * 128 * 64 * 2;
   const size_t w_bytes = static_cast<size_t>(nh) * 64 * 2;
   const int nkb = a.kh_pad / 64;
   const size_t budget = 227 * 1024 - 1024 - a_ring - 2048;  // alignment slack + barriers
-  int w_stages = static_cast<int>(budget / w_bytes);
+  int w_stages;
   int resident = 0;
-  if (w_stages >= nkb) {
-    w_stages = nkb;
+  if (static_cast<size_t>(nkb) * w_bytes <= budget && nkb <= 64) {
+    w_stages = nkb;  // the whole slice stays in shared memory: loaded once
     resident = 1;
+  } else {
+    w_stages = static_cast<int>(budget / (kGW * w_bytes));
+    if (w_stages > 4) w_stages = 4;
+    if (w_stages < 2) return cudaErrorInvalidValue;
   }
-  if (w_stages > 40) w_stages = 40;
-  if (w_stages < 2) return cudaErrorInvalidValue;
-  const size_t smem = 1024 + a_ring + w_stages * w_bytes + (2 * kAStages + 2 * w_stages + 1) * 8 + 16;
+  const size_t smem = 1024 + a_ring + static_cast<size_t>(w_stages) * (resident ? w_bytes : kGW * w_bytes) +
+                      (2 * kAStages + 2 * w_stages + 1) * 8 + 16;
   int tmem_cols = 32;
   while (tmem_cols < 2 * nh) tmem_cols <<= 1;
   auto kfn = lstm_seq_kernel<NCH>;

@@ -26,7 +26,22 @@ n_cta = 120 if a.layer < 3 else 100
 buf = np.zeros((n_cta, a.T, 8), dtype=np.int64)
 n = enc._lib.ie_debug_seq_trace(enc._h, -1, buf.ctypes.data, buf.size)
 print("records", n)
-us = 1.0 / (a.ghz * 1e3)
+us = 1e-3   # trace is in ns (%globaltimer)
+tr_all = buf.astype(np.float64)
+sel = slice(8, a.T - 1)
+pub = tr_all[:, :, 6]          # publish time of every CTA, every step
+pas = tr_all[:, :, 0]          # barrier-passed time
+lead = pub[::2]
+print("global: step period us", np.diff(pas.min(0))[sel].mean() * us)
+print("global: publish spread across CTAs (max-min) us: mean", ((pub.max(0) - pub.min(0))[sel]).mean() * us)
+print("global: last publish(t) -> first barrier pass(t+1) us:", ((pas.min(0)[1:] - pub.max(0)[:-1])[sel]).mean() * us,
+      " -> last pass:", ((pas.max(0)[1:] - pub.max(0)[:-1])[sel]).mean() * us)
+late = (pub - pub.min(0, keepdims=True))[:, sel].mean(1)
+print("global: CTAs publishing latest (cta, mean lag us):", [(int(i), round(late[i] * us, 2)) for i in np.argsort(-late)[:6]])
+ep = (tr_all[:, :, 5] - tr_all[:, :, 4])[:, sel].mean(1)
+print("global: epilogue duration us: mean", ep.mean() * us, "max", ep.max() * us)
+mm = (tr_all[::2, :, 3] - tr_all[::2, :, 2])[:, sel].mean(1)
+print("global: MMA phase (first A landed -> last commit) us: mean", mm.mean() * us, "max", mm.max() * us)
 names = ["0 barrier passed", "1 last A issued", "2 first A landed(MMA)", "3 MMAs issued+commit", "4 tfull seen", "5 epilogue stores done", "6 fenced+bar", "7 gx loads issued"]
 for cta in (0, 1, 2, 59, 119 if n_cta == 120 else 99):
     tr = buf[cta].astype(np.float64)
