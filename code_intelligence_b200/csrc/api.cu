@@ -351,7 +351,7 @@ int run_encoder(ie_encoder* h, const int64_t* ids, const int32_t* lengths, int B
       q.fast_math = h->fast_math;
       q.trace = nullptr;
       if (l == h->trace_layer) {
-        CK(h->trace.reserve(static_cast<size_t>(L.n_cta) * T * 8 * sizeof(long long), true));
+        CK(h->trace.reserve(static_cast<size_t>(L.n_cta) * T * 12 * sizeof(long long), true));
         q.trace = h->trace.as<long long>();
         h->trace_T = T;
         h->trace_ctas = L.n_cta;
@@ -513,10 +513,10 @@ int64_t ie_debug_seq_trace(ie_encoder* h, int32_t layer, long long* out, int64_t
   h->trace_layer = layer;
   if (out == nullptr) return 0;
   const int64_t n = static_cast<int64_t>(h->trace_ctas) * h->trace_T;
-  if (n == 0 || n * 8 > cap) return fail(IE_ERR_STATE, "no trace recorded or buffer too small");
+  if (n == 0 || n * 12 > cap) return fail(IE_ERR_STATE, "no trace recorded or buffer too small");
   cudaSetDevice(h->cfg.device);
   cudaDeviceSynchronize();
-  if (cudaMemcpy(out, h->trace.p, n * 8 * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess)
+  if (cudaMemcpy(out, h->trace.p, n * 12 * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess)
     return fail(IE_ERR_CUDA, "trace copy failed");
   return n;
 }

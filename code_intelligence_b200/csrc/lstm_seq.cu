@@ -62,9 +62,10 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  // optional per-CTA timeline (%globaltimer, ns) of every step: [cta][t][8]; null in production
+  // optional per-CTA timeline (%globaltimer, ns) of every step: [cta][t][12]; null in production
 #define IE_TRACE(slot, tt) do { if (trace) { unsigned long long _g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_g)); \
-    trace[(static_cast<long long>(blockIdx.x) * T + (tt)) * 8 + (slot)] = static_cast<long long>(_g); } } while (0)
+    trace[(static_cast<long long>(blockIdx.x) * T + (tt)) * 12 + (slot)] = static_cast<long long>(_g); } } while (0)
+#define IE_TRACE_VAL(slot, tt, v) do { if (trace) trace[(static_cast<long long>(blockIdx.x) * T + (tt)) * 12 + (slot)] = (v); } while (0)
   const uint32_t crank = cluster_ctarank();  // 0 = leader
   const int pair = blockIdx.x >> 1;
   const unsigned total_ctas = gridDim.x;
@@ -153,17 +154,22 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
       int as = 0, ws = 0;
       uint32_t aph = 0, wph = 0;
       for (int t = 0; t < T; ++t) {
+        long long wa = 0, ww = 0, t_first = 0;
         for (int kb = 0; kb < num_k_blocks; ++kb) {
           const int ja = kb % kGA;   // position inside the current h stage
           const int jw = kb % kGW;   // position inside the current W stage (ring mode)
           if (ja == 0) {
+            const long long c0 = trace ? clock64() : 0;
             mbar_wait(&afull[as], aph);
-            if (kb == 0) IE_TRACE(2, t);
+            if (kb == 0) { IE_TRACE(2, t); t_first = trace ? clock64() : 0; }
+            else if (trace) wa += clock64() - c0;
           }
           if (w_resident) {
             if (t == 0) mbar_wait(&wfull[kb], 0);
           } else if (jw == 0) {
+            const long long c0 = trace ? clock64() : 0;
             mbar_wait(&wfull[ws], wph);
+            if (trace) ww += clock64() - c0;
           }
           tc_fence_after();
           const uint64_t da = umma_desc_sw128(a_base + (as * kGA + ja) * a_bytes);
@@ -182,6 +188,9 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
         }
         umma_commit_pair_mc(tfull, 0x3);
         IE_TRACE(3, t);
+        IE_TRACE_VAL(8, t, wa);                                   // SM cycles waiting for h stages (after the first)
+        IE_TRACE_VAL(9, t, ww);                                   // SM cycles waiting for W stages
+        IE_TRACE_VAL(10, t, trace ? clock64() - t_first : 0);     // SM cycles first h stage -> all MMAs issued
       }
     }
   } else if (warp >= 4) {

@@ -23,7 +23,7 @@ enc.encode_ids(ids)   # warm
 enc._lib.ie_debug_seq_trace(enc._h, a.layer, None, 0)
 enc.encode_ids(ids)
 n_cta = 120 if a.layer < 3 else 100
-buf = np.zeros((n_cta, a.T, 8), dtype=np.int64)
+buf = np.zeros((n_cta, a.T, 12), dtype=np.int64)
 n = enc._lib.ie_debug_seq_trace(enc._h, -1, buf.ctypes.data, buf.size)
 print("records", n)
 us = 1e-3   # trace is in ns (%globaltimer)
@@ -40,6 +40,9 @@ late = (pub - pub.min(0, keepdims=True))[:, sel].mean(1)
 print("global: CTAs publishing latest (cta, mean lag us):", [(int(i), round(late[i] * us, 2)) for i in np.argsort(-late)[:6]])
 ep = (tr_all[:, :, 5] - tr_all[:, :, 4])[:, sel].mean(1)
 print("global: epilogue duration us: mean", ep.mean() * us, "max", ep.max() * us)
+cyc = 1.0 / (a.ghz * 1e3)
+print("global: MMA thread per step (us @%.2f GHz): waiting for h stages %.2f, waiting for W stages %.2f, first-stage->all issued %.2f" % (
+    a.ghz, tr_all[::2, sel, 8].mean() * cyc, tr_all[::2, sel, 9].mean() * cyc, tr_all[::2, sel, 10].mean() * cyc))
 mm = (tr_all[::2, :, 3] - tr_all[::2, :, 2])[:, sel].mean(1)
 print("global: MMA phase (first A landed -> last commit) us: mean", mm.mean() * us, "max", mm.max() * us)
 names = ["0 barrier passed", "1 last A issued", "2 first A landed(MMA)", "3 MMAs issued+commit", "4 tfull seen", "5 epilogue stores done", "6 fenced+bar", "7 gx loads issued"]
