@@ -533,9 +533,10 @@ int ie_encoder_last_phase_ms(ie_encoder* h, float* ms, int32_t cap) {
 }
 
 // debug: cycles to issue / execute iters*4 tcgen05.mma of shape M=128 (mode 0) or M=256 CTA pair (mode 1) x N=n x K=16
-int ie_debug_umma_rate(int32_t mode, int32_t n, int32_t iters, int32_t commit_every, int32_t grid, long long* out2) {
+int ie_debug_umma_rate(int32_t mode, int32_t n, int32_t iters, int32_t commit_every, int32_t grid, int32_t ntiles,
+                       long long* out2) {
   if (out2 == nullptr || n < 16 || n > 256 || n % 16 || iters < 1) return fail(IE_ERR_INVALID, "bad argument");
-  CK(ie::run_umma_rate(mode, n, iters, commit_every, grid < 1 ? 1 : grid, out2));
+  CK(ie::run_umma_rate(mode, n, iters, commit_every, grid < 1 ? 1 : grid, ntiles, out2));
   return IE_OK;
 }
 

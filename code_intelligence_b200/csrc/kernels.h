@@ -76,7 +76,7 @@ struct LstmSeqArgs {
 cudaError_t launch_lstm_seq(const LstmSeqArgs& a, cudaStream_t stream);
 
 // ---- UMMA issue/throughput micro-benchmark (umma_bench.cu, debug) ------------------------------------------------
-cudaError_t run_umma_rate(int mode, int n, int iters, int commit_every, int grid, long long* host_out);
+cudaError_t run_umma_rate(int mode, int n, int iters, int commit_every, int grid, int ntiles, long long* host_out);
 
 // ---- small memory-bound kernels (misc.cu) --------------------------------------------------------
 // ids [B, T] int64 (batch-first, right padded) -> x0 [(T*b_pad), ldx] bf16, time-major rows t*b_pad + b

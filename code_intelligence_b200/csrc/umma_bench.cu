@@ -8,14 +8,14 @@ namespace ie {
 namespace {
 
 // mode 0: cta_group::1, M=128.  One thread issues `iters` groups of 4 MMAs (K = 4 x 16) and one commit per group.
-__global__ void __launch_bounds__(128, 1) umma_rate_kernel(int n, int iters, int commit_every, long long* out) {
+__global__ void __launch_bounds__(128, 1) umma_rate_kernel(int n, int iters, int commit_every, int ntiles, long long* out) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
   __shared__ uint64_t bar;
   __shared__ uint32_t tslot;
-  // zero A (16 KB) and B (n x 128 B) tiles
-  for (int i = threadIdx.x; i < (16384 + n * 128) / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  // zero the operand area: ntiles A tiles (16 KB apart) followed by ntiles B tiles (16 KB apart)
+  for (int i = threadIdx.x; i < (2 * ntiles * 16384) / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
   if (threadIdx.x == 0) {
     mbar_init(&bar, 1);
     fence_barrier_init();
@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(128, 1) umma_rate_kernel(int n, int iters, int
   if (threadIdx.x == 0) {
     const uint32_t idesc = umma_idesc_bf16(128, n);
     const uint64_t da = umma_desc_sw128(smem_u32(smem));
-    const uint64_t db = umma_desc_sw128(smem_u32(smem + 16384));
+    const uint64_t db = umma_desc_sw128(smem_u32(smem + ntiles * 16384));
     uint32_t phase = 0;
     // warm
     for (int k = 0; k < 4; ++k) umma_bf16(tm, da + 2 * k, db + 2 * k, idesc, 1);
@@ -37,8 +37,10 @@ __global__ void __launch_bounds__(128, 1) umma_rate_kernel(int n, int iters, int
     mbar_wait(&bar, phase); phase ^= 1;
     const long long t0 = clock64();
     for (int i = 0; i < iters; ++i) {
+      // ntiles > 1: every group reads a different A / B tile (streaming operands), tiles 16 KB apart
+      const uint64_t off = static_cast<uint64_t>((i % ntiles) * (16384 >> 4));
 #pragma unroll
-      for (int k = 0; k < 4; ++k) umma_bf16(tm, da + 2 * k, db + 2 * k, idesc, 1);
+      for (int k = 0; k < 4; ++k) umma_bf16(tm, da + off + 2 * k, db + off + 2 * k, idesc, 1);
       if ((i + 1) % commit_every == 0 && i + 1 < iters) umma_commit(&bar), mbar_wait(&bar, phase), phase ^= 1;
     }
     const long long t1 = clock64();   // issue done
@@ -53,13 +55,13 @@ __global__ void __launch_bounds__(128, 1) umma_rate_kernel(int n, int iters, int
 }
 
 // mode 1: cta_group::2, M=256, N=n (each CTA holds n/2 rows of B)
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) umma_rate_pair_kernel(int n, int iters, long long* out) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) umma_rate_pair_kernel(int n, int iters, int ntiles, long long* out) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
   __shared__ uint64_t bar;
   __shared__ uint32_t tslot;
-  for (int i = threadIdx.x; i < (16384 + n * 64) / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = threadIdx.x; i < (2 * ntiles * 16384) / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
   if (threadIdx.x == 0) {
     mbar_init(&bar, 1);
     fence_barrier_init();
@@ -74,14 +76,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) umma_rate_pa
   if (cluster_ctarank() == 0 && threadIdx.x == 0) {
     const uint32_t idesc = umma_idesc_bf16(256, n);
     const uint64_t da = umma_desc_sw128(smem_u32(smem));
-    const uint64_t db = umma_desc_sw128(smem_u32(smem + 16384));
+    const uint64_t db = umma_desc_sw128(smem_u32(smem + ntiles * 16384));
     for (int k = 0; k < 4; ++k) umma_bf16_pair(tm, da + 2 * k, db + 2 * k, idesc, 1);
     umma_commit_pair_mc(&bar, 0x3);
     mbar_wait(&bar, 0);
     const long long t0 = clock64();
     for (int i = 0; i < iters; ++i) {
+      const uint64_t off = static_cast<uint64_t>((i % ntiles) * (16384 >> 4));
 #pragma unroll
-      for (int k = 0; k < 4; ++k) umma_bf16_pair(tm, da + 2 * k, db + 2 * k, idesc, 1);
+      for (int k = 0; k < 4; ++k) umma_bf16_pair(tm, da + off + 2 * k, db + off + 2 * k, idesc, 1);
     }
     const long long t1 = clock64();
     umma_commit_pair_mc(&bar, 0x3);
@@ -101,18 +104,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) umma_rate_pa
 }  // namespace
 
 // out[0] = cycles to ISSUE iters*4 MMAs, out[1] = cycles until they have all executed
-cudaError_t run_umma_rate(int mode, int n, int iters, int commit_every, int grid, long long* host_out) {
+cudaError_t run_umma_rate(int mode, int n, int iters, int commit_every, int grid, int ntiles, long long* host_out) {
   long long* d = nullptr;
   cudaError_t e = cudaMalloc(&d, 16);
   if (e != cudaSuccess) return e;
   cudaMemset(d, 0, 16);
-  const size_t smem = 1024 + 16384 + 256 * 128 + 64;
+  if (ntiles < 1) ntiles = 1;
+  if (ntiles > 6) ntiles = 6;
+  const size_t smem = 1024 + static_cast<size_t>(2 * ntiles) * 16384 + 64;
   if (mode == 0) {
     cudaFuncSetAttribute(umma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    umma_rate_kernel<<<grid, 128, smem>>>(n, iters, commit_every > 0 ? commit_every : iters, d);
+    umma_rate_kernel<<<grid, 128, smem>>>(n, iters, commit_every > 0 ? commit_every : iters, ntiles, d);
   } else {
     cudaFuncSetAttribute(umma_rate_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    umma_rate_pair_kernel<<<grid * 2, 128, smem>>>(n, iters, d);
+    umma_rate_pair_kernel<<<grid * 2, 128, smem>>>(n, iters, ntiles, d);
   }
   e = cudaDeviceSynchronize();
   if (e == cudaSuccess) e = cudaMemcpy(host_out, d, 16, cudaMemcpyDeviceToHost);

@@ -99,7 +99,8 @@ int ie_encoder_last_phase_ms(ie_encoder* h, float* ms, int32_t cap);
 int64_t ie_debug_seq_trace(ie_encoder* h, int32_t layer, long long* out, int64_t cap);
 
 /* Debug hook: issue / execution cycles of back-to-back tcgen05.mma (tools/umma_rate.py). */
-int ie_debug_umma_rate(int32_t mode, int32_t n, int32_t iters, int32_t commit_every, int32_t grid, long long* out2);
+int ie_debug_umma_rate(int32_t mode, int32_t n, int32_t iters, int32_t commit_every, int32_t grid, int32_t ntiles,
+                       long long* out2);
 
 /* MLP head.  Replaces sklearn MLPClassifier.predict_proba as called by MLPWrapper.predict_probabilities
  * (py/label_microservice/mlp.py:56-63): relu hidden layers, logistic output (multilabel).
