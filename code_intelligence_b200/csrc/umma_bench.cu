@@ -14,8 +14,8 @@ __global__ void __launch_bounds__(128, 1) umma_rate_kernel(int n, int iters, int
   uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
   __shared__ uint64_t bar;
   __shared__ uint32_t tslot;
-  // zero the operand area: ntiles A tiles (16 KB apart) followed by ntiles B tiles (16 KB apart)
-  for (int i = threadIdx.x; i < (2 * ntiles * 16384) / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  // zero the operand area: ntiles A tiles (16 KB apart) followed by ntiles B tiles (32 KB apart)
+  for (int i = threadIdx.x; i < (ntiles * 49152) / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
   if (threadIdx.x == 0) {
     mbar_init(&bar, 1);
     fence_barrier_init();
@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(128, 1) umma_rate_kernel(int n, int iters, int
       // ntiles > 1: every group reads a different A / B tile (streaming operands), tiles 16 KB apart
       const uint64_t off = static_cast<uint64_t>((i % ntiles) * (16384 >> 4));
 #pragma unroll
-      for (int k = 0; k < 4; ++k) umma_bf16(tm, da + off + 2 * k, db + off + 2 * k, idesc, 1);
+      for (int k = 0; k < 4; ++k) umma_bf16(tm, da + off + 2 * k, db + 2 * off + 2 * k, idesc, 1);
       if ((i + 1) % commit_every == 0 && i + 1 < iters) umma_commit(&bar), mbar_wait(&bar, phase), phase ^= 1;
     }
     const long long t1 = clock64();   // issue done
@@ -61,7 +61,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) umma_rate_pa
   uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
   __shared__ uint64_t bar;
   __shared__ uint32_t tslot;
-  for (int i = threadIdx.x; i < (2 * ntiles * 16384) / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = threadIdx.x; i < (ntiles * 49152) / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
   if (threadIdx.x == 0) {
     mbar_init(&bar, 1);
     fence_barrier_init();
@@ -84,7 +84,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) umma_rate_pa
     for (int i = 0; i < iters; ++i) {
       const uint64_t off = static_cast<uint64_t>((i % ntiles) * (16384 >> 4));
 #pragma unroll
-      for (int k = 0; k < 4; ++k) umma_bf16_pair(tm, da + off + 2 * k, db + off + 2 * k, idesc, 1);
+      for (int k = 0; k < 4; ++k) umma_bf16_pair(tm, da + off + 2 * k, db + 2 * off + 2 * k, idesc, 1);
     }
     const long long t1 = clock64();
     umma_commit_pair_mc(&bar, 0x3);
@@ -110,8 +110,8 @@ cudaError_t run_umma_rate(int mode, int n, int iters, int commit_every, int grid
   if (e != cudaSuccess) return e;
   cudaMemset(d, 0, 16);
   if (ntiles < 1) ntiles = 1;
-  if (ntiles > 6) ntiles = 6;
-  const size_t smem = 1024 + static_cast<size_t>(2 * ntiles) * 16384 + 64;
+  if (ntiles > 4) ntiles = 4;
+  const size_t smem = 1024 + static_cast<size_t>(ntiles) * 49152 + 64;
   if (mode == 0) {
     cudaFuncSetAttribute(umma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     umma_rate_kernel<<<grid, 128, smem>>>(n, iters, commit_every > 0 ? commit_every : iters, ntiles, d);

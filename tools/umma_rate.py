@@ -6,7 +6,7 @@ from code_intelligence_b200 import _lib
 lib = _lib.load()
 out = np.zeros(2, dtype=np.int64)
 iters = 3000
-for ntiles in (1, 6):
+for ntiles in (1, 4):
     for mode, n in [(0, 16), (0, 80), (0, 160), (0, 240), (0, 256), (1, 64), (1, 160), (1, 256)]:
         rc = lib.ie_debug_umma_rate(mode, n, iters, 0, 1, ntiles, out.ctypes.data)
         m = 128 if mode == 0 else 256
