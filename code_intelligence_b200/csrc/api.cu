@@ -210,7 +210,7 @@ int ensure_workspace(ie_encoder* h, int b_pad, int T, bool want_raw) {
   CK(h->pool_last.reserve(pb));
   CK(h->out.reserve(static_cast<size_t>(IE_MAX_BATCH) * 3 * c.emb_sz * sizeof(float)));
   if (want_raw) CK(h->raw.reserve(static_cast<size_t>(b_pad) * T * h->layers.back().out_pad * sizeof(float)));
-  CK(h->step_done.reserve(static_cast<size_t>(c.n_layers) * 256 * sizeof(unsigned)));  // one flag per CTA per layer
+  CK(h->step_done.reserve(static_cast<size_t>(c.n_layers) * T * sizeof(unsigned)));
   return IE_OK;
 }
 
@@ -288,7 +288,7 @@ int run_encoder(ie_encoder* h, const int64_t* ids, const int32_t* lengths, int B
     cudaGetLastError();
     h->seq_checked = 1;
   }
-  if (seq) CK(cudaMemsetAsync(h->step_done.p, 0, static_cast<size_t>(c.n_layers) * 256 * sizeof(unsigned), s));
+  if (seq) CK(cudaMemsetAsync(h->step_done.p, 0, static_cast<size_t>(c.n_layers) * T * sizeof(unsigned), s));
   int cur = 0;
   const __nv_bfloat16* layer_in = h->x0.as<__nv_bfloat16>();
   long long layer_in_ld = h->e_pad;
@@ -345,7 +345,7 @@ int run_encoder(ie_encoder* h, const int64_t* ids, const int32_t* lengths, int B
       ie::LstmSeqArgs q{};
       q.tm_h = a.tm_h; q.tm_w = a.tm_w; q.gx = a.gx; q.y = a.y; q.raw = a.raw;
       q.pool_sum = a.pool_sum; q.pool_max = a.pool_max; q.pool_last = a.pool_last; q.lengths = a.lengths;
-      q.step_done = h->step_done.as<unsigned>() + static_cast<size_t>(l) * 256;
+      q.step_done = h->step_done.as<unsigned>() + static_cast<size_t>(l) * T;
       q.T = T; q.b_pad = b_pad; q.u = L.u; q.n_cta = L.n_cta; q.out_pad = L.out_pad; q.kh_pad = L.kh_pad;
       q.ldy = a.ldy; q.raw_ld = a.raw_ld; q.check_only = 0;
       q.fast_math = h->fast_math;

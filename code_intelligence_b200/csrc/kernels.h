@@ -66,7 +66,7 @@ struct LstmSeqArgs {
   float* pool_max;
   float* pool_last;
   const int* lengths;
-  unsigned* step_done;  // [n_cta] zero-initialised per-CTA published-step flags, laid out [batch half][pair]
+  unsigned* step_done;  // [T] zero-initialised grid-barrier counters
   int T, b_pad, u, n_cta, out_pad, kh_pad;
   long long ldy, raw_ld;
   int check_only;  // 1: only check that the grid can be co-resident

@@ -68,6 +68,7 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
 #define IE_TRACE_VAL(slot, tt, v) do { if (trace) trace[(static_cast<long long>(blockIdx.x) * T + (tt)) * 12 + (slot)] = (v); } while (0)
   const uint32_t crank = cluster_ctarank();  // 0 = leader
   const int pair = blockIdx.x >> 1;
+  const unsigned total_ctas = gridDim.x;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_h);
@@ -94,54 +95,28 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
 
   if (warp == 0) {
     // ---------------- h producer: this CTA's 128 batch rows of h_{t-1}, k-block by k-block ----------------------
-    // Dataflow instead of a grid barrier: columns [64kb, 64kb+64) of h_{t-1} were produced by two or three CTA pairs,
-    // so a k-block is loaded as soon as THOSE pairs have published step t-1.  Every CTA owns one flag (number of
-    // steps published, single writer); the whole warp polls the flags of the CTAs that hold this batch half (a
-    // few coalesced loads), lane 0 issues the TMA loads in k order.
-    const int n_pairs = static_cast<int>(gridDim.x >> 1);
-    const unsigned* flags = step_done + crank * n_pairs;
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int t = 0; t < T; ++t) {
-      int ready_pairs = (t == 0) ? n_pairs : 0;  // pairs [0, ready_pairs) are known to have published h_{t-1}
-      const int row0 = t * kBPad + static_cast<int>(crank) * 128;
-      for (int kb0 = 0; kb0 < num_k_blocks; kb0 += kGA) {
-        const int n = min(kGA, num_k_blocks - kb0);
-        const int last_unit = min(64 * (kb0 + n), out_pad) - 1;
-        const int need = min(n_pairs, last_unit / (2 * NCH * 4) + 1);
-        if (ready_pairs < need) {
-          const long long t0 = clock64();
-          uint32_t spins = 0;
-          while (ready_pairs < need) {
-            int cnt = ready_pairs & ~31;
-            for (int base = cnt; base < n_pairs; base += 32) {
-              const int idx = base + lane;
-              const bool ok = idx >= n_pairs || ld_relaxed(flags + idx) >= static_cast<unsigned>(t);
-              const unsigned m = __ballot_sync(0xffffffffu, ok);
-              if (m == 0xffffffffu) { cnt = base + 32; continue; }
-              cnt = base + __ffs(~m) - 1;
-              break;
-            }
-            ready_pairs = min(cnt, n_pairs);
-            if (((++spins) & 0xFFu) == 0 && (clock64() - t0) > 4000000000ll) __trap();
-          }
-          __threadfence();  // acquire side of the flag handshake (every polling lane), then hand over to lane 0
-          __syncwarp();
-          if (lane == 0) fence_proxy_async();  // order the async-proxy (TMA) reads after the acquire
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = 0; t < T; ++t) {
+        if (t > 0) {
+          wait_flag_ge_relaxed(step_done + (t - 1), total_ctas);  // every CTA has published its slice of h_{t-1}
+          fence_proxy_async();                             // order the async-proxy (TMA) reads after the acquire
         }
-        if (lane == 0) {
-          if (kb0 == 0) IE_TRACE(0, t);
+        IE_TRACE(0, t);
+        const int row0 = t * kBPad + static_cast<int>(crank) * 128;
+        for (int kb0 = 0; kb0 < num_k_blocks; kb0 += kGA) {
+          const int n = min(kGA, num_k_blocks - kb0);
           mbar_wait(&aempty[stage], phase ^ 1);
           if (crank == 0) mbar_arrive_expect_tx(&afull[stage], 2 * n * a_bytes);
           else mbar_arrive_remote(&afull[stage], 0);
           for (int j = 0; j < n; ++j)
             tma_load_2d_pair(a_ring + (stage * kGA + j) * a_bytes, &tm_h, &afull[stage], (kb0 + j) * 64, row0,
                              kEvictNormal);
+          if (++stage == kAStages) { stage = 0; phase ^= 1; }
         }
-        __syncwarp();
-        if (++stage == kAStages) { stage = 0; phase ^= 1; }
+        IE_TRACE(1, t);
       }
-      if (lane == 0) IE_TRACE(1, t);
     }
   } else if (warp == 3) {
     // ---------------- W producer: this CTA's half of the pair's W_hh slice; free-running ahead of h -------------
@@ -304,7 +279,7 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
       named_bar_sync(1, 256);
       if (threadIdx.x == 128) {
         __threadfence();  // cumulative: covers the h stores of all 256 epilogue threads ordered by the barrier
-        st_relaxed(step_done + crank * (gridDim.x >> 1) + pair, static_cast<unsigned>(t + 1));
+        red_relaxed_add(step_done + t, 1u);
         IE_TRACE(6, t);
       }
     }

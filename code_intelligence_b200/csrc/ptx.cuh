@@ -312,9 +312,6 @@ __device__ __forceinline__ void wait_flag_ge_relaxed(const unsigned* p, unsigned
   }
   __threadfence();
 }
-__device__ __forceinline__ void st_relaxed(unsigned* p, unsigned v) {
-  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
 __device__ __forceinline__ void red_relaxed_add(unsigned* p, unsigned v) {
   asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
