@@ -210,7 +210,7 @@ int ensure_workspace(ie_encoder* h, int b_pad, int T, bool want_raw) {
   CK(h->pool_last.reserve(pb));
   CK(h->out.reserve(static_cast<size_t>(IE_MAX_BATCH) * 3 * c.emb_sz * sizeof(float)));
   if (want_raw) CK(h->raw.reserve(static_cast<size_t>(b_pad) * T * h->layers.back().out_pad * sizeof(float)));
-  CK(h->step_done.reserve(static_cast<size_t>(c.n_layers) * T * sizeof(unsigned)));
+  CK(h->step_done.reserve(static_cast<size_t>(c.n_layers) * T * 2 * sizeof(unsigned)));
   return IE_OK;
 }
 
@@ -236,7 +236,7 @@ int run_encoder(ie_encoder* h, const int64_t* ids, const int32_t* lengths, int B
   if (ids == nullptr || (out == nullptr && raw_out == nullptr)) return fail(IE_ERR_INVALID, "null pointer");
   const bool dev = (flags & IE_FLAG_DEVICE_PTRS) != 0;
   const bool pooled = out != nullptr;
-  const int b_pad = B <= 128 ? 128 : 256;
+  const int b_pad = B <= 128 ? 128 : (B <= 256 ? 256 : 512);
   if (static_cast<long long>(b_pad) * T > (1ll << 21))
     return fail(IE_ERR_OOM, "B_pad*T = %lld tokens exceeds the workspace cap; use a smaller batch",
                 static_cast<long long>(b_pad) * T);
@@ -277,7 +277,7 @@ int run_encoder(ie_encoder* h, const int64_t* ids, const int32_t* lengths, int B
 
   const long long rows = static_cast<long long>(T) * b_pad;
   // persistent per-layer recurrent kernel: needs both 128-row halves and every CTA of a layer co-resident
-  bool seq = h->use_seq && b_pad == 256;
+  bool seq = h->use_seq && b_pad >= 256;
   if (seq && !h->seq_checked) {
     for (const Layer& L : h->layers) {
       ie::LstmSeqArgs q{};
@@ -288,7 +288,8 @@ int run_encoder(ie_encoder* h, const int64_t* ids, const int32_t* lengths, int B
     cudaGetLastError();
     h->seq_checked = 1;
   }
-  if (seq) CK(cudaMemsetAsync(h->step_done.p, 0, static_cast<size_t>(c.n_layers) * T * sizeof(unsigned), s));
+  if (b_pad == 512 && !seq) return fail(IE_ERR_STATE, "B > 256 needs the persistent kernel (caller splits the batch)");
+  if (seq) CK(cudaMemsetAsync(h->step_done.p, 0, static_cast<size_t>(c.n_layers) * T * 2 * sizeof(unsigned), s));
   int cur = 0;
   const __nv_bfloat16* layer_in = h->x0.as<__nv_bfloat16>();
   long long layer_in_ld = h->e_pad;
@@ -345,7 +346,7 @@ int run_encoder(ie_encoder* h, const int64_t* ids, const int32_t* lengths, int B
       ie::LstmSeqArgs q{};
       q.tm_h = a.tm_h; q.tm_w = a.tm_w; q.gx = a.gx; q.y = a.y; q.raw = a.raw;
       q.pool_sum = a.pool_sum; q.pool_max = a.pool_max; q.pool_last = a.pool_last; q.lengths = a.lengths;
-      q.step_done = h->step_done.as<unsigned>() + static_cast<size_t>(l) * T;
+      q.step_done = h->step_done.as<unsigned>() + static_cast<size_t>(l) * T * 2;
       q.T = T; q.b_pad = b_pad; q.u = L.u; q.n_cta = L.n_cta; q.out_pad = L.out_pad; q.kh_pad = L.kh_pad;
       q.ldy = a.ldy; q.raw_ld = a.raw_ld; q.check_only = 0;
       q.fast_math = h->fast_math;
@@ -491,7 +492,19 @@ int ie_encoder_encode(ie_encoder* h, const int64_t* ids, const int32_t* lengths,
   // device-pointer mode: `stream` is used verbatim (NULL = the legacy default stream, e.g. torch's default);
   // host-pointer mode: NULL selects the handle's own stream
   cudaStream_t s = (stream || (flags & IE_FLAG_DEVICE_PTRS)) ? static_cast<cudaStream_t>(stream) : h->own_stream;
-  return run_encoder(h, ids, lengths, B, T, out, nullptr, flags, s);
+  if (B > 256 && B <= IE_MAX_BATCH && (!h->use_seq)) {
+    // without the persistent kernel the two 256-row batches are simply run one after the other
+    int rc = run_encoder(h, ids, lengths, 256, T, out, nullptr, flags, s);
+    if (rc != IE_OK) return rc;
+    return run_encoder(h, ids + 256ll * T, lengths + 256, B - 256, T, out + 256ll * 3 * h->cfg.emb_sz, nullptr, flags, s);
+  }
+  int rc = run_encoder(h, ids, lengths, B, T, out, nullptr, flags, s);
+  if (rc == IE_ERR_STATE && B > 256 && !h->use_seq) {  // the co-residency check just turned the persistent kernel off
+    rc = run_encoder(h, ids, lengths, 256, T, out, nullptr, flags, s);
+    if (rc != IE_OK) return rc;
+    return run_encoder(h, ids + 256ll * T, lengths + 256, B - 256, T, out + 256ll * 3 * h->cfg.emb_sz, nullptr, flags, s);
+  }
+  return rc;
 }
 
 int ie_encoder_raw_features(ie_encoder* h, const int64_t* ids, int32_t B, int32_t T, float* raw, int32_t flags,

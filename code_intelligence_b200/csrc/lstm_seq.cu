@@ -31,7 +31,7 @@ constexpr int kGA = 2;       // k-blocks per h stage (32 KB)
 constexpr int kAStages = 4;  // 4 x 32 KB ring of h tiles
 constexpr int kGW = 4;       // k-blocks per W_hh stage (ring mode)
 
-template <int NCH>
+template <int NCH, int NG>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSeqThreads, 1)
 lstm_seq_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ CUtensorMap tm_w,
                 const float* __restrict__ gx, __nv_bfloat16* __restrict__ y, float* __restrict__ raw,
@@ -39,7 +39,9 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
                 const int* __restrict__ lengths, unsigned* __restrict__ step_done, int T, int out_pad, int num_k_blocks,
                 long long ldy, long long raw_ld, int w_stages, int w_resident, int tmem_cols, int fast_math,
                 long long* __restrict__ trace) {
-  constexpr int kBPad = 256;
+  // NG independent 256-row batches ride the same launch (ping-pong): while the epilogue / step barrier of one batch
+  // runs, the tensor pipe works on the other one.  A time slot holds NG*256 rows.
+  constexpr int kBPad = 256 * NG;
   constexpr int NH = NCH * 16;  // W rows this CTA contributes = accumulator columns of one slice
   constexpr int N = 2 * NH;     // accumulator columns of the pair
   extern __shared__ uint8_t smem_raw[];
@@ -57,8 +59,8 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
   uint64_t* aempty = afull + kAStages;        // [kAStages]
   uint64_t* wfull = aempty + kAStages;        // [w_stages]
   uint64_t* wempty = wfull + w_stages;        // [w_stages]
-  uint64_t* tfull = wempty + w_stages;        // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
+  uint64_t* tfull = wempty + w_stages;        // [NG]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + NG);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -83,7 +85,7 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
       mbar_init(&wfull[s], 2);
       mbar_init(&wempty[s], 1);
     }
-    mbar_init(tfull, 1);
+    for (int g = 0; g < NG; ++g) mbar_init(&tfull[g], 1);
     fence_barrier_init();
   }
   cluster_sync();  // barrier inits visible to the peer before any remote arrive; both CTAs reach the 2-CTA alloc
@@ -98,13 +100,14 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = 0; t < T; ++t) {
+      for (int tg = 0; tg < T * NG; ++tg) {
+        const int t = tg / NG, g = tg % NG;
         if (t > 0) {
-          wait_flag_ge_relaxed(step_done + (t - 1), total_ctas);  // every CTA has published its slice of h_{t-1}
+          wait_flag_ge_relaxed(step_done + (tg - NG), total_ctas);  // every CTA has published h_{t-1} of batch g
           fence_proxy_async();                             // order the async-proxy (TMA) reads after the acquire
         }
-        IE_TRACE(0, t);
-        const int row0 = t * kBPad + static_cast<int>(crank) * 128;
+        if (g == 0) IE_TRACE(0, t);
+        const int row0 = t * kBPad + g * 256 + static_cast<int>(crank) * 128;
         for (int kb0 = 0; kb0 < num_k_blocks; kb0 += kGA) {
           const int n = min(kGA, num_k_blocks - kb0);
           mbar_wait(&aempty[stage], phase ^ 1);
@@ -115,7 +118,7 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
                              kEvictNormal);
           if (++stage == kAStages) { stage = 0; phase ^= 1; }
         }
-        IE_TRACE(1, t);
+        if (g == 0) IE_TRACE(1, t);
       }
     }
   } else if (warp == 3) {
@@ -131,7 +134,7 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
       } else {
         int stage = 0;
         uint32_t phase = 0;
-        for (int t = 0; t < T; ++t) {
+        for (int tg = 0; tg < T * NG; ++tg) {
           for (int kb0 = 0; kb0 < num_k_blocks; kb0 += kGW) {
             const int n = min(kGW, num_k_blocks - kb0);
             mbar_wait(&wempty[stage], phase ^ 1);
@@ -153,7 +156,9 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
       const uint32_t w_base = smem_u32(w_ring);
       int as = 0, ws = 0;
       uint32_t aph = 0, wph = 0;
-      for (int t = 0; t < T; ++t) {
+      for (int tg = 0; tg < T * NG; ++tg) {
+        const int t = tg / NG, g = tg % NG;
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(g * N);
         long long wa = 0, ww = 0, t_first = 0;
         for (int kb = 0; kb < num_k_blocks; ++kb) {
           const int ja = kb % kGA;   // position inside the current h stage
@@ -165,7 +170,7 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
             else if (trace) wa += clock64() - c0;
           }
           if (w_resident) {
-            if (t == 0) mbar_wait(&wfull[kb], 0);
+            if (tg == 0) mbar_wait(&wfull[kb], 0);
           } else if (jw == 0) {
             const long long c0 = trace ? clock64() : 0;
             mbar_wait(&wfull[ws], wph);
@@ -175,7 +180,7 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
           const uint64_t da = umma_desc_sw128(a_base + (as * kGA + ja) * a_bytes);
           const uint64_t db = umma_desc_sw128(w_base + (w_resident ? kb : ws * kGW + jw) * w_bytes);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16_pair(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          for (int k = 0; k < 4; ++k) umma_bf16_pair(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
           const bool last = (kb == num_k_blocks - 1);
           if (ja == kGA - 1 || last) {
             umma_commit_pair_mc(&aempty[as], 0x3);
@@ -186,11 +191,11 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
             if (++ws == w_stages) { ws = 0; wph ^= 1; }
           }
         }
-        umma_commit_pair_mc(tfull, 0x3);
-        IE_TRACE(3, t);
-        IE_TRACE_VAL(8, t, wa);                                   // SM cycles waiting for h stages (after the first)
-        IE_TRACE_VAL(9, t, ww);                                   // SM cycles waiting for W stages
-        IE_TRACE_VAL(10, t, trace ? clock64() - t_first : 0);     // SM cycles first h stage -> all MMAs issued
+        umma_commit_pair_mc(&tfull[g], 0x3);
+        if (g == 0) IE_TRACE(3, t);
+        if (g == 0) IE_TRACE_VAL(8, t, wa);                                   // SM cycles waiting for h stages (after the first)
+        if (g == 0) IE_TRACE_VAL(9, t, ww);                                   // SM cycles waiting for W stages
+        if (g == 0) IE_TRACE_VAL(10, t, trace ? clock64() - t_first : 0);     // SM cycles first h stage -> all issued
       }
     }
   } else if (warp >= 4) {
@@ -198,89 +203,97 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
     const int e = warp - 4;
     const int q = e & 3;                      // TMEM lane quarter == warp % 4
     const int half = e >> 2;                  // which NH columns of the pair's N this warp handles
-    const int row = static_cast<int>(crank) * 128 + q * 32 + lane;   // batch row
+    const int row = static_cast<int>(crank) * 128 + q * 32 + lane;   // row inside a 256-row batch
     const int unit0 = pair * (2 * NCH * 4) + half * (NCH * 4);       // first hidden unit of this thread
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(half * NH);
-    const int len = (pool_sum != nullptr) ? lengths[row] : 1;
-    float cst[NCH * 4];
+    int len[NG];
+    float cst[NG][NCH * 4];
 #pragma unroll
-    for (int i = 0; i < NCH * 4; ++i) cst[i] = 0.0f;
+    for (int g = 0; g < NG; ++g) {
+      len[g] = (pool_sum != nullptr) ? lengths[g * 256 + row] : 1;
+#pragma unroll
+      for (int i = 0; i < NCH * 4; ++i) cst[g][i] = 0.0f;
+    }
 
     for (int t = 0; t < T; ++t) {
-      const float4* gxp = reinterpret_cast<const float4*>(gx + (static_cast<long long>(t) * kBPad + row) * (4ll * out_pad) +
-                                                          4ll * unit0);
-      float4 gxr[NCH * 4];
 #pragma unroll
-      for (int i = 0; i < NCH * 4; ++i) gxr[i] = __ldg(gxp + i);
-      if (threadIdx.x == 128) IE_TRACE(7, t);
-      if (t + 1 < T) {
-        // pull the next step's Gx rows from HBM into L2 while this step streams, so that the loads at the top of
-        // step t+1 are short and do not queue in front of the step barrier traffic
-        const char* nx = reinterpret_cast<const char*>(gxp) + static_cast<long long>(kBPad) * out_pad * 16ll;
+      for (int g = 0; g < NG; ++g) {
+        const int brow = g * 256 + row;  // row inside the time slot
+        const float4* gxp = reinterpret_cast<const float4*>(gx + (static_cast<long long>(t) * kBPad + brow) * (4ll * out_pad) +
+                                                            4ll * unit0);
+        float4 gxr[NCH * 4];
 #pragma unroll
-        for (int i = 0; i < (NCH * 64 + 127) / 128 + 1; ++i) prefetch_l2(nx + i * 128);
-      }
+        for (int i = 0; i < NCH * 4; ++i) gxr[i] = __ldg(gxp + i);
+        if (threadIdx.x == 128 && g == 0) IE_TRACE(7, t);
+        if (t + 1 < T) {
+          // pull the next step's Gx rows from HBM into L2 while this step streams, so that the loads at the top of
+          // step t+1 are short and do not queue in front of the step barrier traffic
+          const char* nx = reinterpret_cast<const char*>(gxp) + static_cast<long long>(kBPad) * out_pad * 16ll;
+#pragma unroll
+          for (int i = 0; i < (NCH * 64 + 127) / 128 + 1; ++i) prefetch_l2(nx + i * 128);
+        }
 
-      mbar_wait(tfull, static_cast<uint32_t>(t & 1));
-      tc_fence_after();
-      if (threadIdx.x == 128) IE_TRACE(4, t);
-      __nv_bfloat16* yrow = y + (static_cast<long long>(t + 1) * kBPad + row) * ldy + unit0;
+        mbar_wait(&tfull[g], static_cast<uint32_t>(t & 1));
+        tc_fence_after();
+        if (threadIdx.x == 128 && g == 0) IE_TRACE(4, t);
+        __nv_bfloat16* yrow = y + (static_cast<long long>(t + 1) * kBPad + brow) * ldy + unit0;
 #pragma unroll
-      for (int ch = 0; ch < NCH; ++ch) {
-        uint32_t r[16];
-        __syncwarp();
-        tmem_ld16(taddr + ch * 16, r);
-        tmem_ld_wait();
-        float hn[4];
+        for (int ch = 0; ch < NCH; ++ch) {
+          uint32_t r[16];
+          __syncwarp();
+          tmem_ld16(taddr + g * N + ch * 16, r);
+          tmem_ld_wait();
+          float hn[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float4 gq = gxr[ch * 4 + j];
-          const float zi = __uint_as_float(r[4 * j + 0]) + gq.x;
-          const float zf = __uint_as_float(r[4 * j + 1]) + gq.y;
-          const float zg = __uint_as_float(r[4 * j + 2]) + gq.z;
-          const float zo = __uint_as_float(r[4 * j + 3]) + gq.w;
-          float cn;
-          if (fast_math) {
-            cn = sigmoid_fast(zf) * cst[ch * 4 + j] + sigmoid_fast(zi) * tanh_fast(zg);
-            hn[j] = sigmoid_fast(zo) * tanh_fast(cn);
-          } else {
-            cn = sigmoid_acc(zf) * cst[ch * 4 + j] + sigmoid_acc(zi) * tanh_acc(zg);
-            hn[j] = sigmoid_acc(zo) * tanh_acc(cn);
+          for (int j = 0; j < 4; ++j) {
+            const float4 gq = gxr[ch * 4 + j];
+            const float zi = __uint_as_float(r[4 * j + 0]) + gq.x;
+            const float zf = __uint_as_float(r[4 * j + 1]) + gq.y;
+            const float zg = __uint_as_float(r[4 * j + 2]) + gq.z;
+            const float zo = __uint_as_float(r[4 * j + 3]) + gq.w;
+            float cn;
+            if (fast_math) {
+              cn = sigmoid_fast(zf) * cst[g][ch * 4 + j] + sigmoid_fast(zi) * tanh_fast(zg);
+              hn[j] = sigmoid_fast(zo) * tanh_fast(cn);
+            } else {
+              cn = sigmoid_acc(zf) * cst[g][ch * 4 + j] + sigmoid_acc(zi) * tanh_acc(zg);
+              hn[j] = sigmoid_acc(zo) * tanh_acc(cn);
+            }
+            cst[g][ch * 4 + j] = cn;
           }
-          cst[ch * 4 + j] = cn;
-        }
-        *reinterpret_cast<uint2*>(yrow + ch * 4) = make_uint2(pack_bf16x2(hn[0], hn[1]), pack_bf16x2(hn[2], hn[3]));
-        if (raw != nullptr) {
-          float4* rp = reinterpret_cast<float4*>(raw + (static_cast<long long>(row) * T + t) * raw_ld + unit0 + ch * 4);
-          *rp = make_float4(hn[0], hn[1], hn[2], hn[3]);
-        }
-        if (pool_sum != nullptr && t < len) {
-          const long long po = static_cast<long long>(row) * out_pad + unit0 + ch * 4;
-          float4* ps = reinterpret_cast<float4*>(pool_sum + po);
-          float4* pm = reinterpret_cast<float4*>(pool_max + po);
-          float4 s, m;
-          if (t == 0) {
-            s = make_float4(hn[0], hn[1], hn[2], hn[3]);
-            m = s;
-          } else {
-            s = *ps;
-            m = *pm;
-            s.x += hn[0]; s.y += hn[1]; s.z += hn[2]; s.w += hn[3];
-            m.x = fmaxf(m.x, hn[0]); m.y = fmaxf(m.y, hn[1]); m.z = fmaxf(m.z, hn[2]); m.w = fmaxf(m.w, hn[3]);
+          *reinterpret_cast<uint2*>(yrow + ch * 4) = make_uint2(pack_bf16x2(hn[0], hn[1]), pack_bf16x2(hn[2], hn[3]));
+          if (raw != nullptr) {
+            float4* rp = reinterpret_cast<float4*>(raw + (static_cast<long long>(brow) * T + t) * raw_ld + unit0 + ch * 4);
+            *rp = make_float4(hn[0], hn[1], hn[2], hn[3]);
           }
-          *ps = s;
-          *pm = m;
-          if (t == len - 1) *reinterpret_cast<float4*>(pool_last + po) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+          if (pool_sum != nullptr && t < len[g]) {
+            const long long po = static_cast<long long>(brow) * out_pad + unit0 + ch * 4;
+            float4* ps = reinterpret_cast<float4*>(pool_sum + po);
+            float4* pm = reinterpret_cast<float4*>(pool_max + po);
+            float4 s, m;
+            if (t == 0) {
+              s = make_float4(hn[0], hn[1], hn[2], hn[3]);
+              m = s;
+            } else {
+              s = *ps;
+              m = *pm;
+              s.x += hn[0]; s.y += hn[1]; s.z += hn[2]; s.w += hn[3];
+              m.x = fmaxf(m.x, hn[0]); m.y = fmaxf(m.y, hn[1]); m.z = fmaxf(m.z, hn[2]); m.w = fmaxf(m.w, hn[3]);
+            }
+            *ps = s;
+            *pm = m;
+            if (t == len[g] - 1) *reinterpret_cast<float4*>(pool_last + po) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+          }
         }
-      }
-      // publish: TMEM reads are done (the next step's MMAs may overwrite the accumulator) and h_t is visible
-      if (threadIdx.x == 128) IE_TRACE(5, t);
-      tc_fence_before();
-      named_bar_sync(1, 256);
-      if (threadIdx.x == 128) {
-        __threadfence();  // cumulative: covers the h stores of all 256 epilogue threads ordered by the barrier
-        red_relaxed_add(step_done + t, 1u);
-        IE_TRACE(6, t);
+        // publish: TMEM reads are done (the batch's next MMAs may overwrite its accumulator) and h_t is visible
+        if (threadIdx.x == 128 && g == 0) IE_TRACE(5, t);
+        tc_fence_before();
+        named_bar_sync(1, 256);
+        if (threadIdx.x == 128) {
+          __threadfence();  // cumulative: covers the h stores of all 256 epilogue threads ordered by the barrier
+          red_relaxed_add(step_done + t * NG + g, 1u);
+          if (g == 0) IE_TRACE(6, t);
+        }
       }
     }
   }
@@ -294,7 +307,7 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
   }
 }
 
-template <int NCH>
+template <int NCH, int NG>
 cudaError_t launch_seq_t(const LstmSeqArgs& a, cudaStream_t stream) {
   const int nh = NCH * 16;
   const size_t a_ring = static_cast<size_t>(kAStages) * kGA * 128 * 64 * 2;
@@ -312,10 +325,10 @@ cudaError_t launch_seq_t(const LstmSeqArgs& a, cudaStream_t stream) {
     if (w_stages < 2) return cudaErrorInvalidValue;
   }
   const size_t smem = 1024 + a_ring + static_cast<size_t>(w_stages) * (resident ? w_bytes : kGW * w_bytes) +
-                      (2 * kAStages + 2 * w_stages + 1) * 8 + 16;
+                      (2 * kAStages + 2 * w_stages + 2) * 8 + 16;
   int tmem_cols = 32;
-  while (tmem_cols < 2 * nh) tmem_cols <<= 1;
-  auto kfn = lstm_seq_kernel<NCH>;
+  while (tmem_cols < NG * 2 * nh) tmem_cols <<= 1;
+  auto kfn = lstm_seq_kernel<NCH, NG>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -346,18 +359,15 @@ cudaError_t launch_seq_t(const LstmSeqArgs& a, cudaStream_t stream) {
 
 // a.check_only != 0: only verify that the whole grid can be co-resident (no launch)
 cudaError_t launch_lstm_seq(const LstmSeqArgs& a, cudaStream_t stream) {
-  if (a.u % 4 || a.u < 4 || a.b_pad != 256 || a.kh_pad % 64 || a.n_cta % 2) return cudaErrorInvalidValue;
+  if (a.u % 4 || a.u < 4 || (a.b_pad != 256 && a.b_pad != 512) || a.kh_pad % 64 || a.n_cta % 2)
+    return cudaErrorInvalidValue;
+#define IE_SEQ_CASE(n)                                                                    \
+  case n: return a.b_pad == 512 ? launch_seq_t<n, 2>(a, stream) : launch_seq_t<n, 1>(a, stream);
   switch (a.u / 4) {
-    case 1: return launch_seq_t<1>(a, stream);
-    case 2: return launch_seq_t<2>(a, stream);
-    case 3: return launch_seq_t<3>(a, stream);
-    case 4: return launch_seq_t<4>(a, stream);
-    case 5: return launch_seq_t<5>(a, stream);
-    case 6: return launch_seq_t<6>(a, stream);
-    case 7: return launch_seq_t<7>(a, stream);
-    case 8: return launch_seq_t<8>(a, stream);
+    IE_SEQ_CASE(1) IE_SEQ_CASE(2) IE_SEQ_CASE(3) IE_SEQ_CASE(4) IE_SEQ_CASE(5) IE_SEQ_CASE(6) IE_SEQ_CASE(7) IE_SEQ_CASE(8)
     default: return cudaErrorInvalidValue;
   }
+#undef IE_SEQ_CASE
 }
 
 }  // namespace ie

@@ -36,7 +36,8 @@ extern "C" {
 
 #define IE_FLAG_DEVICE_PTRS 1
 
-#define IE_MAX_BATCH 256 /* rows per ie_encoder_encode call (two 128-row UMMA tiles) */
+#define IE_MAX_BATCH 512 /* rows per ie_encoder_encode call: up to two 256-row batches ride one launch (each a CTA-pair
+                            M=256 UMMA tile); they share the kernel, not their results */
 
 typedef struct ie_encoder ie_encoder;
 typedef struct ie_mlp ie_mlp;

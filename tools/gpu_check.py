@@ -100,6 +100,11 @@ def check_n3b():
             _enc_parity(4, 800, 2400, 60000, 256, 96, min_len=16, scale=1.0)]
 
 
+def check_dual():
+    # B > 256: two 256-row batches ride one persistent launch (ping-pong)
+    return [_enc_parity(3, 96, 200, 500, 300, 19, min_len=1), _enc_parity(4, 800, 2400, 60000, 512, 64, min_len=8)]
+
+
 def check_speed():
     """B=256, T=512 R4 with device-resident inputs: per-encode CUDA-event time."""
     import numpy as np
@@ -131,7 +136,7 @@ def check_speed():
     return out
 
 
-CHECKS = dict(gemm=check_gemm, tiny=check_tiny, r4_small=check_r4_small, n3=check_n3, n3b=check_n3b, speed=check_speed)
+CHECKS = dict(gemm=check_gemm, tiny=check_tiny, r4_small=check_r4_small, n3=check_n3, n3b=check_n3b, dual=check_dual, speed=check_speed)
 
 if __name__ == '__main__':
     ap = argparse.ArgumentParser()
