@@ -55,16 +55,21 @@ __global__ void __launch_bounds__(128, 1) umma_rate_kernel(int n, int iters, int
 }
 
 // mode 1: cta_group::2, M=256, N=n (each CTA holds n/2 rows of B)
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) umma_rate_pair_kernel(int n, int iters, int ntiles, long long* out) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) umma_rate_pair_kernel(int n, int iters, int ntiles, int mimic, long long* out) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
   __shared__ uint64_t bar;
+  __shared__ uint64_t done_bar;   // a barrier whose phase 0 has completed: waiting on it returns at once
+  __shared__ uint64_t sink_bar;   // receives commits nobody waits for
   __shared__ uint32_t tslot;
   for (int i = threadIdx.x; i < (ntiles * 49152) / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
   if (threadIdx.x == 0) {
     mbar_init(&bar, 1);
+    mbar_init(&done_bar, 1);
+    mbar_init(&sink_bar, 1);
     fence_barrier_init();
+    mbar_arrive(&done_bar);
   }
   fence_proxy_async();
   cluster_sync();
@@ -83,8 +88,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) umma_rate_pa
     const long long t0 = clock64();
     for (int i = 0; i < iters; ++i) {
       const uint64_t off = static_cast<uint64_t>((i % ntiles) * (16384 >> 4));
+      if (mimic & 1) { mbar_wait(&done_bar, 0); mbar_wait(&done_bar, 0); }
+      if (mimic & 2) tc_fence_after();
 #pragma unroll
-      for (int k = 0; k < 4; ++k) umma_bf16_pair(tm, da + off + 2 * k, db + 2 * off + 2 * k, idesc, 1);
+      for (int k = 0; k < 4; ++k) umma_bf16_pair(tm, da + off + 2 * k, db + 2 * off + 2 * k, idesc, (i | k) != 0);
+      if (mimic & 4) umma_commit_pair_mc(&sink_bar, 0x3);
+      if (mimic & 8) umma_commit_pair_mc(&sink_bar, 0x3);
     }
     const long long t1 = clock64();
     umma_commit_pair_mc(&bar, 0x3);
@@ -117,7 +126,7 @@ cudaError_t run_umma_rate(int mode, int n, int iters, int commit_every, int grid
     umma_rate_kernel<<<grid, 128, smem>>>(n, iters, commit_every > 0 ? commit_every : iters, ntiles, d);
   } else {
     cudaFuncSetAttribute(umma_rate_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    umma_rate_pair_kernel<<<grid * 2, 128, smem>>>(n, iters, ntiles, d);
+    umma_rate_pair_kernel<<<grid * 2, 128, smem>>>(n, iters, ntiles, commit_every, d);
   }
   e = cudaDeviceSynchronize();
   if (e == cudaSuccess) e = cudaMemcpy(host_out, d, 16, cudaMemcpyDeviceToHost);
