@@ -14,6 +14,8 @@
 //   warp 1      UMMA issuer : tcgen05.mma kind::f16 M=128 N=bn K=16, accumulators in TMEM (double buffered)
 //   warp 2      TMEM allocator
 //   warps 4..7  epilogue    : tcgen05.ld -> +bias -> activation -> global stores; overlaps the next tile's MMAs
+#include <cstdlib>
+
 #include "kernels.h"
 #include "ptx.cuh"
 
@@ -182,6 +184,178 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
+// ----------------------------------------------------------------------------------------------
+// CTA-pair variant (tcgen05 cta_group::2): a cluster of two CTAs on one TPC computes a 256 x bn tile.  CTA r loads
+// rows [128r, +128) of the A tile and rows [r*bn/2, +bn/2) of the B tile; one M=256 UMMA per K=16 slice feeds both
+// tensor cores, so each SM reads A (4 KB) + half of B per instruction instead of A + all of B -- the single-CTA
+// kernel above is bound by that shared-memory operand traffic (~68 % tensor-pipe activity, profiles/README.md).
+// ----------------------------------------------------------------------------------------------
+template <typename OutT, int ACT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                      OutT* __restrict__ D, const float* __restrict__ bias, int m_store, int n_store, long long ldd,
+                      int num_m_blocks /* of 256 rows */, int num_n_blocks, int num_k_blocks, int bn, int stages,
+                      int panel) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+
+  const uint32_t a_bytes = kBlockM * kBlockK * 2;
+  const uint32_t b_bytes = static_cast<uint32_t>(bn / 2) * kBlockK * 2;   // this CTA's half of the B tile
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(stages) * stage_bytes);
+  uint64_t* full_bar = bars;                   // leader's copy is live: 2 arrivals + both CTAs' bytes
+  uint64_t* empty_bar = bars + stages;         // per CTA, arrival = the leader's multicast commit
+  uint64_t* tfull_bar = bars + 2 * stages;     // per CTA
+  uint64_t* tempty_bar = bars + 2 * stages + 2;  // leader's copy is live: one arrival per CTA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * stages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full_bar[s], 2);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 2);
+    }
+    fence_barrier_init();
+  }
+  cluster_sync();
+  if (warp == 2) tmem_alloc_pair(tmem_slot, 512);
+  tc_fence_before();
+  cluster_sync();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_tiles = num_m_blocks * num_n_blocks;
+  const int panel_tiles = panel * num_n_blocks;
+  auto decode = [&](int tile, int& m_blk, int& n_blk) {
+    const int p = tile / panel_tiles;
+    const int r = tile - p * panel_tiles;
+    const int m0 = p * panel;
+    const int mcnt = min(panel, num_m_blocks - m0);
+    n_blk = r / mcnt;
+    m_blk = m0 + (r - n_blk * mcnt);
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        int m_blk, n_blk;
+        decode(tile, m_blk, n_blk);
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
+          if (crank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * stage_bytes);
+          else mbar_arrive_remote(&full_bar[stage], 0);
+          tma_load_2d_pair(sa, &tmA, &full_bar[stage], kb * kBlockK, m_blk * 256 + static_cast<int>(crank) * kBlockM,
+                           kEvictNormal);
+          tma_load_2d_pair(sa + a_bytes, &tmB, &full_bar[stage], kb * kBlockK,
+                           n_blk * bn + static_cast<int>(crank) * (bn / 2), kEvictLast);
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (crank == 0 && lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(256, bn);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * bn);
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
+          const uint64_t da = umma_desc_sw128(sa);
+          const uint64_t db = umma_desc_sw128(sa + a_bytes);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) umma_bf16_pair(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          umma_commit_pair_mc(&empty_bar[stage], 0x3);
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_pair_mc(&tfull_bar[acc], 0x3);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp - 4;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      int m_blk, n_blk;
+      decode(tile, m_blk, n_blk);
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const int row = m_blk * 256 + static_cast<int>(crank) * kBlockM + q * 32 + lane;
+      const bool row_ok = row < m_store;
+      OutT* drow = D + static_cast<long long>(row) * ldd;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * bn);
+      for (int c = 0; c < bn; c += 16) {
+        uint32_t r[16];
+        tmem_ld16(taddr + c, r);
+        tmem_ld_wait();
+        const int n = n_blk * bn + c;
+        if (row_ok && n < n_store) {
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float x = __uint_as_float(r[j]);
+            if (bias != nullptr) x += __ldg(bias + n + j);
+            if (ACT == 1) x = fmaxf(x, 0.0f);
+            if (ACT == 2) x = sigmoid_acc(x);
+            v[j] = x;
+          }
+          if constexpr (sizeof(OutT) == 4) {
+            float4* dst = reinterpret_cast<float4*>(drow + n);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else {
+            uint4* dst = reinterpret_cast<uint4*>(drow + n);
+            dst[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                                pack_bf16x2(v[6], v[7]));
+            dst[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]),
+                                pack_bf16x2(v[14], v[15]));
+          }
+        }
+      }
+      // this CTA's 128 epilogue threads are done with accumulator `acc`: one arrival per CTA at the leader
+      tc_fence_before();
+      named_bar_sync(2, 128);
+      if (threadIdx.x == 128) {
+        if (crank == 0) mbar_arrive(&tempty_bar[acc]);
+        else mbar_arrive_remote(&tempty_bar[acc], 0);
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  cluster_sync();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, 512);
+  }
+}
+
 }  // namespace
 
 size_t gemm_smem_bytes(int bn, int stages) {
@@ -199,6 +373,51 @@ cudaError_t launch_gemm_bf16(const GemmArgs& g, cudaStream_t stream) {
   if (e != cudaSuccess) return e;
   e = make_tmap_bf16_2d(&tmB, g.b, g.k_pad, g.n_pad, g.ldb, kBlockK, g.bn);
   if (e != cudaSuccess) return e;
+
+  static int use_pair = -1;
+  if (use_pair < 0) {
+    const char* e = getenv("IE_GEMM_PAIR");
+    use_pair = e ? atoi(e) : 1;
+  }
+  const int sms0 = g.num_sms > 0 ? g.num_sms : 148;
+  if (use_pair && g.m_pad % 256 == 0 && g.bn % 16 == 0 && (g.m_pad / 256) * (g.n_pad / g.bn) >= sms0 / 2) {
+    // CTA-pair path: M = 256 tiles
+    CUtensorMap tmBh;
+    e = make_tmap_bf16_2d(&tmBh, g.b, g.k_pad, g.n_pad, g.ldb, kBlockK, g.bn / 2);
+    if (e != cudaSuccess) return e;
+    int stages = 8;
+    auto pair_smem = [&](int st) {
+      return 1024 + static_cast<size_t>(st) * (kBlockM * kBlockK * 2 + (g.bn / 2) * kBlockK * 2) + (2 * st + 4) * 8 + 16;
+    };
+    while (stages > 2 && pair_smem(stages) > 227 * 1024) --stages;
+    const size_t smem = pair_smem(stages);
+    const int num_m_blocks = g.m_pad / 256;
+    const int num_n_blocks = g.n_pad / g.bn;
+    const int num_k_blocks = g.k_pad / kBlockK;
+    const int grid = 2 * (sms0 / 2);
+    int panel = sms0 / 4;
+    if (panel < 1) panel = 1;
+#define IE_LAUNCH_PAIR(OUT, ACT)                                                                                  \
+  do {                                                                                                            \
+    auto kfn = gemm_bf16_pair_kernel<OUT, ACT>;                                                                   \
+    e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));           \
+    if (e != cudaSuccess) return e;                                                                               \
+    kfn<<<grid, kGemmThreads, smem, stream>>>(tmA, tmBh, reinterpret_cast<OUT*>(g.d), g.bias, g.m_store,          \
+                                              g.n_store, g.ldd, num_m_blocks, num_n_blocks, num_k_blocks, g.bn,   \
+                                              stages, panel);                                                     \
+  } while (0)
+    if (g.out_bf16) {
+      if (g.act == 0) IE_LAUNCH_PAIR(__nv_bfloat16, 0);
+      else if (g.act == 1) IE_LAUNCH_PAIR(__nv_bfloat16, 1);
+      else IE_LAUNCH_PAIR(__nv_bfloat16, 2);
+    } else {
+      if (g.act == 0) IE_LAUNCH_PAIR(float, 0);
+      else if (g.act == 1) IE_LAUNCH_PAIR(float, 1);
+      else IE_LAUNCH_PAIR(float, 2);
+    }
+#undef IE_LAUNCH_PAIR
+    return cudaGetLastError();
+  }
 
   int stages = 6;
   while (stages > 2 && gemm_smem_bytes(g.bn, stages) > 227 * 1024) --stages;
