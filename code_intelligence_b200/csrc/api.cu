@@ -94,7 +94,7 @@ struct ie_encoder {
   DevBuf trace;           // debug timeline of one layer of the persistent kernel (ie_debug_seq_trace)
   int trace_layer = -1;
   int trace_T = 0, trace_ctas = 0;
-  int fast_math = 0;      // IE_FAST_MATH / ie_config.flags bit 0: tanh.approx gates in the persistent kernel
+  int fast_math = 1;      // tanh.approx gates in the persistent kernel (ie_config.flags & IE_CFG_ACCURATE_GATES: off)
   int use_seq = 1;        // persistent per-layer kernel (lstm_seq.cu) when B_pad == 256 and the grid is co-resident
   int seq_checked = 0;    // co-residency verified for every layer
   long long y_ld = 0;
@@ -428,7 +428,7 @@ int ie_encoder_create(const ie_config* cfg, ie_encoder** out) {
   h->cfg = *cfg;
   h->num_sms = sms;
   if (const char* e = getenv("IE_SEQ")) h->use_seq = atoi(e);
-  h->fast_math = (cfg->flags & 1) ? 1 : 0;
+  h->fast_math = (cfg->flags & IE_CFG_ACCURATE_GATES) ? 0 : 1;
   if (const char* e = getenv("IE_FAST_MATH")) h->fast_math = atoi(e);
   int rc = plan_layers(h);
   if (rc != IE_OK) { delete h; return rc; }

@@ -36,6 +36,10 @@ extern "C" {
 
 #define IE_FLAG_DEVICE_PTRS 1
 
+/* ie_config.flags */
+#define IE_CFG_ACCURATE_GATES 1 /* ex2+rcp sigmoid/tanh (abs err ~1e-7) instead of the default single-MUFU          */
+                                /* tanh.approx.f32 gates (rel err 2^-11; no measurable effect on the parity metrics) */
+
 #define IE_MAX_BATCH 512 /* rows per ie_encoder_encode call: up to two 256-row batches ride one launch (each a CTA-pair
                             M=256 UMMA tile); they share the kernel, not their results */
 
@@ -53,7 +57,7 @@ typedef struct ie_config {
   int32_t vocab_sz; /* 60000 */
   int32_t pad_idx;  /* 1 (inference.py:36 learn.data.pad_idx) */
   int32_t device;   /* CUDA device ordinal */
-  int32_t flags;    /* reserved, 0 */
+  int32_t flags;    /* IE_CFG_* bits, 0 = defaults */
 } ie_config;
 
 int ie_version(void);

@@ -173,10 +173,12 @@ def test_edge_cases_and_errors(r4):
     want = R.encode_single(ref, np.array([2]))
     _assert_parity(one, want)
     np.testing.assert_allclose(one[0, :800], one[0, 800:1600])                 # mean == max == last for T=1
-    docs = R.synthetic_ids(257, 6, seed=3)                                     # B > IE_MAX_BATCH is sliced
-    ids, lengths = _pad(docs)
+    docs = R.synthetic_ids(600, 6, seed=3, min_len=2)                          # B > IE_MAX_BATCH (512) is sliced;
+    ids, lengths = _pad(docs)                                                  # 257..512 rows ride one launch
     got = enc.encode_ids(ids, lengths)
-    np.testing.assert_array_equal(got[256], enc.encode_ids(ids[256:], lengths[256:])[0])
+    np.testing.assert_array_equal(got[256], enc.encode_ids(ids[256:257], lengths[256:257])[0])
+    np.testing.assert_array_equal(got[:257], enc.encode_ids(ids[:257], lengths[:257]))
+    np.testing.assert_array_equal(got[512:], enc.encode_ids(ids[512:], lengths[512:]))
     with pytest.raises(ValueError):
         enc.encode_ids(ids[:2], np.array([7, 1], dtype=np.int32))              # length > T
     with pytest.raises(ValueError):
@@ -202,6 +204,10 @@ def test_full_size_batch_properties(r4):
     np.testing.assert_array_equal(enc.encode_ids(ids[perm], lengths)[np.argsort(perm)], a)      # row equivariance
     short = np.full(256, 100, dtype=np.int32)                                                   # prefix property
     np.testing.assert_array_equal(enc.encode_ids(ids, short), enc.encode_ids(ids[:, :100].copy(), short))
+    ids2 = np.concatenate([ids, ids[::-1]])                                                     # two batches per launch
+    b = enc.encode_ids(ids2, np.full(512, 512, dtype=np.int32))
+    np.testing.assert_array_equal(b[:256], a)
+    np.testing.assert_array_equal(b[256:], a[::-1])
     want = R.encode_padded(ref, ids[:6], lengths[:6])                                           # ~10 s of CPU
     m = _assert_parity(a[:6], want)
     print("full-size slice", m)
