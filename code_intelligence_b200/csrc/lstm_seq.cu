@@ -1,17 +1,20 @@
-// Persistent recurrent kernel: ALL T timesteps of one LSTM layer in one launch (the same arithmetic as lstm.cu, which
-// stays as the fallback; reference call sites: Issue_Embeddings/flask_app/inference.py:56-57, :66-68, pooling :239).
+// Persistent recurrent kernel: ALL T timesteps of one LSTM layer in one launch, for one or two independent batches of 256
+// rows (the same arithmetic as lstm.cu, which stays as the fallback; reference call sites:
+// Issue_Embeddings/flask_app/inference.py:56-57, :66-68, pooling :239).
 //
-// Why (profiles/README.md, round 1): the per-step kernel is bound by bytes delivered from L2 to the SMs
-// (196 MB per step ~ 12 TB/s chip wide) plus ~9 us of launch / prologue / epilogue that cannot overlap because step
-// t+1 needs every CTA's h_t.  This kernel
+// Why (profiles/README.md, round 1): with one launch per timestep the recurrence ran at 23.7 us per step: the
+// cta_group::1 M=128,N=80 UMMAs use a third of the tensor pipe (an M=128 MMA costs ~128-170 cycles whatever N is) and
+// ~9 us of launch / prologue / epilogue per step cannot overlap because step t+1 needs every CTA's h_t.  This kernel
 //   * pairs CTAs (cluster of 2 on one TPC) into one M=256 tensor core (tcgen05 cta_group::2): CTA r of a pair
 //     holds batch rows [128r, 128r+128) and HALF of the pair's W_hh slice, so per step an SM ingests
 //     128 x K of h plus 2u x K of W instead of 256 x K plus 4u x K  (1.0 MB instead of 1.63 MB at H=2400);
 //   * keeps c_t in registers, barriers / TMEM / tensor maps alive across steps, and prefetches the next step's W_hh
-//     k-blocks (which do not depend on h_t) through their own ring while the epilogue and the grid barrier run;
-//   * replaces the kernel boundary by a grid-scope counter per step: epilogue threads store h_t, fence, and one
-//     thread per CTA does red.release; the h producer of every CTA spins (bounded) on ld.acquire, then
-//     fence.proxy.async, then issues the TMA loads of h_t.
+//     k-blocks (which do not depend on h_t) through their own ring while the epilogue and the step barrier run;
+//   * replaces the kernel boundary by a grid-scope counter per (step, batch): epilogue threads store h_t, CTA barrier,
+//     one thread fences and does red.add; the h producer of every CTA spins (bounded) with relaxed loads, fences,
+//     fence.proxy.async, then issues the TMA loads of h_t;
+//   * NG = 2: two independent 256-row batches alternate inside the launch (own TMEM accumulator, c registers and
+//     counters), so the tensor pipe works on one batch while the other is in its epilogue / barrier phase.
 // All CTAs must be co-resident (grid <= SMs, 1 CTA/SM; checked with cudaOccupancyMaxActiveClusters by the caller).
 //
 // Warp roles per CTA (384 threads): 0 = h (A) producer, 1 = UMMA issuer (leader CTA only), 2 = TMEM allocator,
