@@ -290,6 +290,9 @@ int run_encoder(ie_encoder* h, const int64_t* ids, const int32_t* lengths, int B
   }
   if (b_pad == 512 && !seq) return fail(IE_ERR_STATE, "B > 256 needs the persistent kernel (caller splits the batch)");
   if (seq) CK(cudaMemsetAsync(h->step_done.p, 0, static_cast<size_t>(c.n_layers) * T * 2 * sizeof(unsigned), s));
+  // slot 0 of both hidden-state rings is h_{-1} = 0; a previous call with another B_pad may have written these rows
+  for (int i = 0; i < 2; ++i)
+    CK(cudaMemsetAsync(h->y[i].p, 0, static_cast<size_t>(b_pad) * h->y_ld * sizeof(__nv_bfloat16), s));
   int cur = 0;
   const __nv_bfloat16* layer_in = h->x0.as<__nv_bfloat16>();
   long long layer_in_ld = h->e_pad;
@@ -324,6 +327,7 @@ int run_encoder(ie_encoder* h, const int64_t* ids, const int32_t* lengths, int B
     CK(ie::make_tmap_bf16_2d(&a.tm_h, ybuf, L.kh_pad, static_cast<uint64_t>(rows + b_pad), h->y_ld, 64, 128));
     CK(ie::make_tmap_bf16_2d(&a.tm_w, L.w_hh.p, L.kh_pad, 4ull * L.out_pad, L.kh_pad, 64, 4 * L.u));
     a.cluster = L.cluster;
+    a.fast_math = h->fast_math;
     CK(ie::make_tmap_bf16_2d(&a.tm_hs, ybuf, L.kh_pad, static_cast<uint64_t>(rows + b_pad), h->y_ld, 64,
                              128 / L.cluster));
     a.gx = h->gx.as<float>();

@@ -158,15 +158,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             v[j] = x;
           }
           if constexpr (sizeof(OutT) == 4) {
-            float4* dst = reinterpret_cast<float4*>(drow + n);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            for (int j = 0; j < 2; ++j)
+              st_global_v8(drow + n + 8 * j, __float_as_uint(v[8 * j]), __float_as_uint(v[8 * j + 1]),
+                           __float_as_uint(v[8 * j + 2]), __float_as_uint(v[8 * j + 3]), __float_as_uint(v[8 * j + 4]),
+                           __float_as_uint(v[8 * j + 5]), __float_as_uint(v[8 * j + 6]), __float_as_uint(v[8 * j + 7]));
           } else {
-            uint4* dst = reinterpret_cast<uint4*>(drow + n);
-            dst[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
-                                pack_bf16x2(v[6], v[7]));
-            dst[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]),
-                                pack_bf16x2(v[14], v[15]));
+            st_global_v8(drow + n, pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                         pack_bf16x2(v[6], v[7]), pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]),
+                         pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
           }
         }
       }
@@ -324,15 +324,15 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             v[j] = x;
           }
           if constexpr (sizeof(OutT) == 4) {
-            float4* dst = reinterpret_cast<float4*>(drow + n);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            for (int j = 0; j < 2; ++j)
+              st_global_v8(drow + n + 8 * j, __float_as_uint(v[8 * j]), __float_as_uint(v[8 * j + 1]),
+                           __float_as_uint(v[8 * j + 2]), __float_as_uint(v[8 * j + 3]), __float_as_uint(v[8 * j + 4]),
+                           __float_as_uint(v[8 * j + 5]), __float_as_uint(v[8 * j + 6]), __float_as_uint(v[8 * j + 7]));
           } else {
-            uint4* dst = reinterpret_cast<uint4*>(drow + n);
-            dst[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
-                                pack_bf16x2(v[6], v[7]));
-            dst[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]),
-                                pack_bf16x2(v[14], v[15]));
+            st_global_v8(drow + n, pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                         pack_bf16x2(v[6], v[7]), pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]),
+                         pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
           }
         }
       }

@@ -48,6 +48,7 @@ struct LstmStepArgs {
   int u;       // hidden units per CTA (multiple of 4)
   int n_cta;   // out_pad / u
   int cluster; // CTAs per cluster sharing the h tiles by TMA multicast (1, 2, 4 or 8; divides n_cta)
+  int fast_math; // 1: single-MUFU tanh.approx gates (same as the persistent kernel)
   int out_pad;
   int kh_pad;  // multiple of 64
   long long ldy;

@@ -35,7 +35,7 @@ lstm_step_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant
                  const __grid_constant__ CUtensorMap tm_w, const float* __restrict__ gx, float* __restrict__ cstate, __nv_bfloat16* __restrict__ y,
                  float* __restrict__ raw, float* __restrict__ pool_sum, float* __restrict__ pool_max,
                  float* __restrict__ pool_last, const int* __restrict__ lengths, int t, int T, int b_pad,
-                 int out_pad, int num_k_blocks, long long ldy, long long raw_ld, int tmem_cols) {
+                 int out_pad, int num_k_blocks, long long ldy, long long raw_ld, int tmem_cols, int fast_math) {
   constexpr int U = NCH * 4;  // hidden units per CTA
   constexpr int N = U * 4;    // accumulator columns per M tile
   extern __shared__ uint8_t smem_raw[];
@@ -161,12 +161,14 @@ lstm_step_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant
         const float zf = __uint_as_float(r[4 * j + 1]) + gq.y;
         const float zg = __uint_as_float(r[4 * j + 2]) + gq.z;
         const float zo = __uint_as_float(r[4 * j + 3]) + gq.w;
-        const float ig = sigmoid_acc(zi);
-        const float fg = sigmoid_acc(zf);
-        const float gg = tanh_acc(zg);
-        const float og = sigmoid_acc(zo);
-        cn[j] = fg * cprev[j] + ig * gg;
-        hn[j] = og * tanh_acc(cn[j]);
+        // same expressions (and association) as lstm_seq.cu so that both kernels give identical bits
+        if (fast_math) {
+          cn[j] = sigmoid_fast(zf) * cprev[j] + sigmoid_fast(zi) * tanh_fast(zg);
+          hn[j] = sigmoid_fast(zo) * tanh_fast(cn[j]);
+        } else {
+          cn[j] = sigmoid_acc(zf) * cprev[j] + sigmoid_acc(zi) * tanh_acc(zg);
+          hn[j] = sigmoid_acc(zo) * tanh_acc(cn[j]);
+        }
       }
       cp[ch] = make_float4(cn[0], cn[1], cn[2], cn[3]);
       *reinterpret_cast<uint2*>(yrow + ch * 4) = make_uint2(pack_bf16x2(hn[0], hn[1]), pack_bf16x2(hn[2], hn[3]));
@@ -237,7 +239,7 @@ cudaError_t launch_step_t(const LstmStepArgs& a, cudaStream_t stream) {
   cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kfn, a.tm_h, a.tm_hs, a.tm_w, a.gx, a.c, a.y, a.raw, a.pool_sum, a.pool_max,
                             a.pool_last, a.lengths, a.t, a.T, a.b_pad, a.out_pad, a.kh_pad / 64, a.ldy, a.raw_ld,
-                            tmem_cols);
+                            tmem_cols, a.fast_math);
 }
 
 }  // namespace

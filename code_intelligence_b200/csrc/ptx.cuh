@@ -295,6 +295,15 @@ __device__ __forceinline__ float tanh_fast(float x) {
 }
 __device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
 
+// 256-bit global store (sm_100): one full 32-byte sector per instruction, so the L2 never sees a partial-sector
+// write (the 128-bit stores of the first GEMM epilogue caused read-modify-write fills: DRAM reads ~ output bytes)
+__device__ __forceinline__ void st_global_v8(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e,
+                                             uint32_t f, uint32_t g, uint32_t h) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d),
+               "r"(e), "r"(f), "r"(g), "r"(h)
+               : "memory");
+}
+
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ unsigned ld_relaxed(const unsigned* p) {
   unsigned v;
