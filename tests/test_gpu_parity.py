@@ -209,7 +209,7 @@ def test_full_size_batch_properties(r4):
     np.testing.assert_array_equal(b[:256], a)
     np.testing.assert_array_equal(b[256:], a[::-1])
     want = R.encode_padded(ref, ids[:6], lengths[:6])                                           # ~10 s of CPU
-    m = _assert_parity(a[:6], want)
+    m = _assert_parity(a[:6], want, cc_min=0.97)   # centring over 6 issues only: noisier than the batch-wide metric
     print("full-size slice", m)
 
 
