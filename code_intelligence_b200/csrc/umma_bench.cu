@@ -91,7 +91,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) umma_rate_pa
       if (mimic & 1) { mbar_wait(&done_bar, 0); mbar_wait(&done_bar, 0); }
       if (mimic & 2) tc_fence_after();
 #pragma unroll
-      for (int k = 0; k < 4; ++k) umma_bf16_pair(tm, da + off + 2 * k, db + 2 * off + 2 * k, idesc, (i | k) != 0);
+      for (int k = 0; k < 4; ++k) {
+        // bit4: two independent accumulators, alternating per MMA (two interleaved dependency chains)
+        const uint32_t td = (mimic & 16) ? tm + static_cast<uint32_t>(((i * 4 + k) & 1) * 256) : tm;
+        umma_bf16_pair(td, da + off + 2 * k, db + 2 * off + 2 * k, idesc, (i | k) != 0);
+      }
       if (mimic & 4) umma_commit_pair_mc(&sink_bar, 0x3);
       if (mimic & 8) umma_commit_pair_mc(&sink_bar, 0x3);
     }

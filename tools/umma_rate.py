@@ -14,10 +14,15 @@ for ntiles in (1, 4):
         per_sm = 4096 + (n if mode == 0 else n // 2) * 32
         print(f"ntiles={ntiles} M={m} N={n:3d}: rc={rc} exec {out[1]/(iters*4):7.1f} cyc/MMA (tensor floor {ideal:.0f}); local smem operand bytes/MMA {per_sm} -> {per_sm/(out[1]/(iters*4)):.1f} B/clk")
 
-print("pair M=256 N=160, loop mimicking the recurrent kernel's issue thread (bit0: 2 barrier waits, bit1: tcgen05 fence, bit2: 1 commit, bit3: 2nd commit per 4 MMAs)")
-for mimic in (0, 1, 2, 4, 12, 3, 7, 15):
+print("(bit4 = two interleaved accumulators) pair M=256 N=160, loop mimicking the recurrent kernel's issue thread (bit0: 2 barrier waits, bit1: tcgen05 fence, bit2: 1 commit, bit3: 2nd commit per 4 MMAs)")
+for mimic in (0, 16, 15, 31):
     rc = lib.ie_debug_umma_rate(1, 160, iters, mimic, 1, 4, out.ctypes.data)
     print(f"  mimic={mimic:2d}: rc={rc} issue {out[0]/(iters*4):7.1f}  exec {out[1]/(iters*4):7.1f} cyc/MMA")
-for mimic in (0, 15):
+for mimic in (0, 16):
     rc = lib.ie_debug_umma_rate(1, 160, iters, mimic, 60, 4, out.ctypes.data)
     print(f"  60 pairs mimic={mimic:2d}: rc={rc} exec {out[1]/(iters*4):7.1f} cyc/MMA")
+
+for n in (160, 240, 256):
+    for mimic in (0, 16):
+        rc = lib.ie_debug_umma_rate(1, n, iters, mimic, 1, 4, out.ctypes.data)
+        print(f"  pair N={n} mimic={mimic:2d}: exec {out[1]/(iters*4):7.1f} cyc/MMA")
