@@ -78,13 +78,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) umma_rate_pa
   cluster_sync();
   tc_fence_after();
   const uint32_t tm = tslot;
-  if (cluster_ctarank() == 0 && threadIdx.x == 0) {
+  // bit5 of mimic: a second issuing thread (warp 1) runs the same loop on its own accumulator and barrier
+  __shared__ uint64_t bar2;
+  if (threadIdx.x == 0) { mbar_init(&bar2, 1); fence_barrier_init(); }
+  cluster_sync();
+  const bool issuer0 = cluster_ctarank() == 0 && threadIdx.x == 0;
+  const bool issuer1 = cluster_ctarank() == 0 && threadIdx.x == 32 && (mimic & 32);
+  if (issuer0 || issuer1) {
+    uint64_t* mybar = issuer0 ? &bar : &bar2;
     const uint32_t idesc = umma_idesc_bf16(256, n);
     const uint64_t da = umma_desc_sw128(smem_u32(smem));
     const uint64_t db = umma_desc_sw128(smem_u32(smem + ntiles * 16384));
-    for (int k = 0; k < 4; ++k) umma_bf16_pair(tm, da + 2 * k, db + 2 * k, idesc, 1);
-    umma_commit_pair_mc(&bar, 0x3);
-    mbar_wait(&bar, 0);
+    const uint32_t tacc = issuer0 ? tm : tm + 256;
+    for (int k = 0; k < 4; ++k) umma_bf16_pair(tacc, da + 2 * k, db + 2 * k, idesc, 1);
+    umma_commit_pair_mc(mybar, 0x3);
+    mbar_wait(mybar, 0);
     const long long t0 = clock64();
     for (int i = 0; i < iters; ++i) {
       const uint64_t off = static_cast<uint64_t>((i % ntiles) * (16384 >> 4));
@@ -93,20 +101,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) umma_rate_pa
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         // bit4: two independent accumulators, alternating per MMA (two interleaved dependency chains)
-        const uint32_t td = (mimic & 16) ? tm + static_cast<uint32_t>(((i * 4 + k) & 1) * 256) : tm;
+        const uint32_t td = (mimic & 16) ? tacc + static_cast<uint32_t>(((i * 4 + k) & 1) * 128) : tacc;
         umma_bf16_pair(td, da + off + 2 * k, db + 2 * off + 2 * k, idesc, (i | k) != 0);
       }
       if (mimic & 4) umma_commit_pair_mc(&sink_bar, 0x3);
       if (mimic & 8) umma_commit_pair_mc(&sink_bar, 0x3);
     }
     const long long t1 = clock64();
-    umma_commit_pair_mc(&bar, 0x3);
-    mbar_wait(&bar, 1);
+    umma_commit_pair_mc(mybar, 0x3);
+    mbar_wait(mybar, 1);
     const long long t2 = clock64();
-    if (blockIdx.x == 0) { out[0] = t1 - t0; out[1] = t2 - t0; }
+    if (blockIdx.x == 0 && issuer0) { out[0] = t1 - t0; out[1] = t2 - t0; }
   } else if (threadIdx.x == 0) {
     mbar_wait(&bar, 0);
     mbar_wait(&bar, 1);
+    if (mimic & 32) { mbar_wait(&bar2, 0); mbar_wait(&bar2, 1); }
   }
   __syncwarp();
   tc_fence_before();
