@@ -143,8 +143,9 @@ int plan_layers(ie_encoder* h) {
     L.kin_pad = prev_pad;
     L.kh_pad = static_cast<int>(round_up(L.out_pad, 64));
     prev_pad = L.kh_pad;
-    // cluster size for the h-tile multicast: largest of 8/4/2/1 dividing n_cta (IE_STEP_CLUSTER overrides)
-    int want = 4;
+    // cluster size for the h-tile multicast in the per-step fallback kernel: largest of 8/4/2/1 <= want dividing n_cta.
+    // Measured (profiles/README.md): multicast changes nothing there, so the default is no clusters.
+    int want = 1;
     if (const char* e = getenv("IE_STEP_CLUSTER")) want = atoi(e);
     L.cluster = 1;
     for (int cs = 8; cs >= 1; cs >>= 1)

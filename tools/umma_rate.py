@@ -27,8 +27,3 @@ for n in (160, 240, 256):
         rc = lib.ie_debug_umma_rate(1, n, iters, mimic, 1, 4, out.ctypes.data)
         print(f"  pair N={n} mimic={mimic:2d}: exec {out[1]/(iters*4):7.1f} cyc/MMA")
 
-print("two issuing threads (bit5), each 4*iters MMAs on its own accumulator: cycles per MMA of ONE thread (half that per MMA overall)")
-for n in (128, 160, 256):
-    for mimic in (0, 32):
-        rc = lib.ie_debug_umma_rate(1, n, iters, mimic, 1, 4, out.ctypes.data)
-        print(f"  pair N={n} mimic={mimic:2d}: rc={rc} exec {out[1]/(iters*4):7.1f} cyc/MMA per issuing thread")
