@@ -128,3 +128,26 @@ def test_distributed_bulk_gloo_world2(tmp_path):
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
         assert "ok" in o
+
+
+def test_features_dictionary_and_writers(tmp_path):
+    """Output contract of get_all_issue_text (py/code_intelligence/embeddings.py:116-118): features[:, :1600]."""
+    from code_intelligence_b200 import embeddings as E
+
+    class FakeWrapper:            # stands in for InferenceWrapper: the contract under test is the slicing / writers
+        def df_to_embedding(self, df, bs=100):
+            return np.arange(len(df) * 2400, dtype=np.float32).reshape(len(df), 2400)
+
+    issues = [dict(title=f"t{i}", body="b", labels=[f"l{i}"], num=i + 1) for i in range(3)]
+    d = E.issues_to_features(FakeWrapper(), issues)
+    assert d["features"].shape == (3, 1600) and d["labels"] == [["l0"], ["l1"], ["l2"]] and d["nums"] == [1, 2, 3]
+    np.testing.assert_array_equal(d["features"][1], np.arange(2400, 2400 + 1600, dtype=np.float32))
+    with pytest.raises(ValueError):
+        E.issues_to_features(FakeWrapper(), [])
+    E.save_features(str(tmp_path / "f.dpkl"), d)
+    import dill
+    back = dill.load(open(tmp_path / "f.dpkl", "rb"))
+    np.testing.assert_array_equal(back["features"], d["features"])
+    out = E.save_embeddings(str(tmp_path / "emb"), np.ones((2, 2400)))
+    arr = np.load(out) if out.endswith(".npy") else None
+    assert arr is None or (arr.dtype == np.dtype("<f4") and arr.shape == (2, 2400))
