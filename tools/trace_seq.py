@@ -8,6 +8,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--T", type=int, default=128)
 ap.add_argument("--layer", type=int, default=1)
 ap.add_argument("--ghz", type=float, default=1.9)
+ap.add_argument("--B", type=int, default=256)
 a = ap.parse_args()
 g = torch.Generator().manual_seed(1)
 dims = [((800 if l == 0 else 2400), (2400 if l != 3 else 800)) for l in range(4)]
@@ -18,7 +19,7 @@ for i, o in dims:
     u = lambda *s: ((torch.rand(*s, generator=g) * 2 - 1) * k).numpy()
     layers.append(dict(w_ih=u(4 * o, i), w_hh=u(4 * o, o), b_ih=u(4 * o), b_hh=u(4 * o)))
 enc = IssueEncoder().load_weights(emb, layers)
-ids = torch.randint(2, 60000, (256, a.T), generator=g, dtype=torch.int64).numpy()
+ids = torch.randint(2, 60000, (a.B, a.T), generator=g, dtype=torch.int64).numpy()
 enc.encode_ids(ids)   # warm
 enc._lib.ie_debug_seq_trace(enc._h, a.layer, None, 0)
 enc.encode_ids(ids)
