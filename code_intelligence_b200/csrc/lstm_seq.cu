@@ -34,7 +34,7 @@ constexpr int kGA = 2;       // k-blocks per h stage (32 KB)
 constexpr int kAStages = 4;  // 4 x 32 KB ring of h tiles
 constexpr int kGW = 4;       // k-blocks per W_hh stage (ring mode)
 
-template <int NCH, int NG>
+template <int NCH, int NG, bool POOL>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSeqThreads, 1)
 lstm_seq_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ CUtensorMap tm_w,
                 const float* __restrict__ gx, __nv_bfloat16* __restrict__ y, float* __restrict__ raw,
@@ -211,11 +211,17 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(half * NH);
     int len[NG];
     float cst[NG][NCH * 4];
+    // last layer (POOL): the masked concat-pool accumulators of inference.py:239 live in registers for all T steps and
+    // are written once at the end (a global read-modify-write per step put ~2.5 us on the step's critical path)
+    constexpr int PN = POOL ? NCH * 4 : 1;
+    float psum[NG][PN], pmax[NG][PN], plast[NG][PN];
 #pragma unroll
     for (int g = 0; g < NG; ++g) {
-      len[g] = (pool_sum != nullptr) ? lengths[g * 256 + row] : 1;
+      len[g] = POOL ? lengths[g * 256 + row] : 1;
 #pragma unroll
       for (int i = 0; i < NCH * 4; ++i) cst[g][i] = 0.0f;
+#pragma unroll
+      for (int i = 0; i < PN; ++i) { psum[g][i] = 0.0f; pmax[g][i] = -INFINITY; plast[g][i] = 0.0f; }
     }
 
     for (int t = 0; t < T; ++t) {
@@ -269,23 +275,16 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
             float4* rp = reinterpret_cast<float4*>(raw + (static_cast<long long>(brow) * T + t) * raw_ld + unit0 + ch * 4);
             *rp = make_float4(hn[0], hn[1], hn[2], hn[3]);
           }
-          if (pool_sum != nullptr && t < len[g]) {
-            const long long po = static_cast<long long>(brow) * out_pad + unit0 + ch * 4;
-            float4* ps = reinterpret_cast<float4*>(pool_sum + po);
-            float4* pm = reinterpret_cast<float4*>(pool_max + po);
-            float4 s, m;
-            if (t == 0) {
-              s = make_float4(hn[0], hn[1], hn[2], hn[3]);
-              m = s;
-            } else {
-              s = *ps;
-              m = *pm;
-              s.x += hn[0]; s.y += hn[1]; s.z += hn[2]; s.w += hn[3];
-              m.x = fmaxf(m.x, hn[0]); m.y = fmaxf(m.y, hn[1]); m.z = fmaxf(m.z, hn[2]); m.w = fmaxf(m.w, hn[3]);
+          if constexpr (POOL) {
+            if (t < len[g]) {
+              const bool is_last = (t == len[g] - 1);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                psum[g][ch * 4 + j] += hn[j];
+                pmax[g][ch * 4 + j] = fmaxf(pmax[g][ch * 4 + j], hn[j]);
+                if (is_last) plast[g][ch * 4 + j] = hn[j];
+              }
             }
-            *ps = s;
-            *pm = m;
-            if (t == len[g] - 1) *reinterpret_cast<float4*>(pool_last + po) = make_float4(hn[0], hn[1], hn[2], hn[3]);
           }
         }
         // publish: TMEM reads are done (the batch's next MMAs may overwrite its accumulator) and h_t is visible
@@ -296,6 +295,21 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
           __threadfence();  // cumulative: covers the h stores of all 256 epilogue threads ordered by the barrier
           red_relaxed_add(step_done + t * NG + g, 1u);
           if (g == 0) IE_TRACE(6, t);
+        }
+      }
+    }
+    if constexpr (POOL) {
+#pragma unroll
+      for (int g = 0; g < NG; ++g) {
+        const long long po = static_cast<long long>(g * 256 + row) * out_pad + unit0;
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+          *reinterpret_cast<float4*>(pool_sum + po + ch * 4) =
+              make_float4(psum[g][ch * 4], psum[g][ch * 4 + 1], psum[g][ch * 4 + 2], psum[g][ch * 4 + 3]);
+          *reinterpret_cast<float4*>(pool_max + po + ch * 4) =
+              make_float4(pmax[g][ch * 4], pmax[g][ch * 4 + 1], pmax[g][ch * 4 + 2], pmax[g][ch * 4 + 3]);
+          *reinterpret_cast<float4*>(pool_last + po + ch * 4) =
+              make_float4(plast[g][ch * 4], plast[g][ch * 4 + 1], plast[g][ch * 4 + 2], plast[g][ch * 4 + 3]);
         }
       }
     }
@@ -310,7 +324,7 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
   }
 }
 
-template <int NCH, int NG>
+template <int NCH, int NG, bool POOL>
 cudaError_t launch_seq_t(const LstmSeqArgs& a, cudaStream_t stream) {
   const int nh = NCH * 16;
   const size_t a_ring = static_cast<size_t>(kAStages) * kGA * 128 * 64 * 2;
@@ -331,7 +345,7 @@ cudaError_t launch_seq_t(const LstmSeqArgs& a, cudaStream_t stream) {
                       (2 * kAStages + 2 * w_stages + 2) * 8 + 16;
   int tmem_cols = 32;
   while (tmem_cols < NG * 2 * nh) tmem_cols <<= 1;
-  auto kfn = lstm_seq_kernel<NCH, NG>;
+  auto kfn = lstm_seq_kernel<NCH, NG, POOL>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -364,8 +378,11 @@ cudaError_t launch_seq_t(const LstmSeqArgs& a, cudaStream_t stream) {
 cudaError_t launch_lstm_seq(const LstmSeqArgs& a, cudaStream_t stream) {
   if (a.u % 4 || a.u < 4 || (a.b_pad != 256 && a.b_pad != 512) || a.kh_pad % 64 || a.n_cta % 2)
     return cudaErrorInvalidValue;
-#define IE_SEQ_CASE(n)                                                                    \
-  case n: return a.b_pad == 512 ? launch_seq_t<n, 2>(a, stream) : launch_seq_t<n, 1>(a, stream);
+#define IE_SEQ_CASE(n)                                                                                   \
+  case n:                                                                                                \
+    if (a.pool_sum != nullptr)                                                                           \
+      return a.b_pad == 512 ? launch_seq_t<n, 2, true>(a, stream) : launch_seq_t<n, 1, true>(a, stream); \
+    return a.b_pad == 512 ? launch_seq_t<n, 2, false>(a, stream) : launch_seq_t<n, 1, false>(a, stream);
   switch (a.u / 4) {
     IE_SEQ_CASE(1) IE_SEQ_CASE(2) IE_SEQ_CASE(3) IE_SEQ_CASE(4) IE_SEQ_CASE(5) IE_SEQ_CASE(6) IE_SEQ_CASE(7) IE_SEQ_CASE(8)
     default: return cudaErrorInvalidValue;
