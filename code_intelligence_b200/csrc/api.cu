@@ -98,7 +98,6 @@ struct ie_encoder {
   int use_seq = 1;        // persistent per-layer kernel (lstm_seq.cu) when B_pad == 256 and the grid is co-resident
   int seq_checked = 0;    // co-residency verified for every layer
   long long y_ld = 0;
-  size_t y_bytes_zeroed = 0;
   cudaStream_t own_stream = nullptr;
   int64_t launches = 0;
   // phase boundary events of the last encode call: start, gather, (gemm_l, steps_l) x L, finalize

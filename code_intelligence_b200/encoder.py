@@ -40,7 +40,6 @@ class IssueEncoder:
         h = C.c_void_p()
         check(self._lib.ie_encoder_create(C.byref(cfg), C.byref(h)))
         self._h = h
-        self._pinned = {}
 
     # ------------------------------------------------------------------ lifetime
     def close(self):
