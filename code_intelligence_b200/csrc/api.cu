@@ -237,9 +237,12 @@ int run_encoder(ie_encoder* h, const int64_t* ids, const int32_t* lengths, int B
   const bool dev = (flags & IE_FLAG_DEVICE_PTRS) != 0;
   const bool pooled = out != nullptr;
   const int b_pad = B <= 128 ? 128 : (B <= 256 ? 256 : 512);
-  if (static_cast<long long>(b_pad) * T > (1ll << 21))
-    return fail(IE_ERR_OOM, "B_pad*T = %lld tokens exceeds the workspace cap; use a smaller batch",
-                static_cast<long long>(b_pad) * T);
+  // workspace cap (tokens per call); IE_MAX_TOKENS lowers it, e.g. to exercise the caller's batch-halving loop
+  long long cap = 1ll << 21;
+  if (const char* e = getenv("IE_MAX_TOKENS")) cap = std::max(128ll, atoll(e));
+  if (static_cast<long long>(b_pad) * T > cap)
+    return fail(IE_ERR_OOM, "B_pad*T = %lld tokens exceeds the workspace cap %lld; use a smaller batch",
+                static_cast<long long>(b_pad) * T, cap);
   CK(cudaSetDevice(c.device));
   int rc = ensure_workspace(h, b_pad, T, raw_out != nullptr);
   if (rc != IE_OK) return rc;

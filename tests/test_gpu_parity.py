@@ -213,6 +213,28 @@ def test_full_size_batch_properties(r4):
     print("full-size slice", m)
 
 
+def test_oom_halving_and_threads(r4, monkeypatch):
+    """IE_ERR_OOM surfaces as RuntimeError, so the reference's batch-halving loop (py/code_intelligence/inference.py:214-223)
+    keeps working; one handle may be driven from several host threads (calls are serialised inside the library)."""
+    import threading
+    enc, _ = r4
+    docs = R.synthetic_ids(40, 24, seed=13, min_len=4)
+    want = enc.encode_id_list(docs, bs=40, min_batches_rule=False)
+    monkeypatch.setenv("IE_MAX_TOKENS", str(128 * 24))           # only B_pad = 128 fits: 40 -> 20 ... still 128-padded
+    np.testing.assert_array_equal(enc.encode_id_list(docs, bs=40, min_batches_rule=False), want)
+    monkeypatch.setenv("IE_MAX_TOKENS", "128")                    # nothing with T > 1 fits: the loop gives up at bs == 1
+    with pytest.raises(Exception):
+        enc.encode_id_list(docs, bs=4, min_batches_rule=False)
+    monkeypatch.delenv("IE_MAX_TOKENS")
+    outs = [None] * 4
+    def work(i):
+        outs[i] = enc.encode_id_list(docs[i * 10:(i + 1) * 10], bs=10, min_batches_rule=False)
+    ths = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    [t.start() for t in ths]
+    [t.join() for t in ths]
+    np.testing.assert_array_equal(np.concatenate(outs), want)
+
+
 # ------------------------------------------------------------------------------------------------ python surface
 def test_inference_wrapper_surface(tmp_path):
     from code_intelligence_b200.inference import InferenceWrapper, text_endpoint_bytes
