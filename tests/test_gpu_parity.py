@@ -218,10 +218,10 @@ def test_oom_halving_and_threads(r4, monkeypatch):
     keeps working; one handle may be driven from several host threads (calls are serialised inside the library)."""
     import threading
     enc, _ = r4
-    docs = R.synthetic_ids(40, 24, seed=13, min_len=4)
-    want = enc.encode_id_list(docs, bs=40, min_batches_rule=False)
-    monkeypatch.setenv("IE_MAX_TOKENS", str(128 * 24))           # only B_pad = 128 fits: 40 -> 20 ... still 128-padded
-    np.testing.assert_array_equal(enc.encode_id_list(docs, bs=40, min_batches_rule=False), want)
+    docs = R.synthetic_ids(300, 24, seed=13, min_len=4)
+    want = enc.encode_id_list(docs, bs=300, min_batches_rule=False)
+    monkeypatch.setenv("IE_MAX_TOKENS", str(128 * 24))           # only B_pad = 128 fits: bs 300 -> 150 -> 75
+    np.testing.assert_array_equal(enc.encode_id_list(docs, bs=300, min_batches_rule=False), want)
     monkeypatch.setenv("IE_MAX_TOKENS", "128")                    # nothing with T > 1 fits: the loop gives up at bs == 1
     with pytest.raises(Exception):
         enc.encode_id_list(docs, bs=4, min_batches_rule=False)
