@@ -15,7 +15,7 @@ LIB_PATH = _PKG / "libissue_emb_b200.so"
 
 IE_OK, IE_ERR_INVALID, IE_ERR_CUDA, IE_ERR_OOM, IE_ERR_STATE, IE_ERR_TOKEN = 0, -1, -2, -3, -4, -5
 IE_FLAG_DEVICE_PTRS = 1
-IE_MAX_BATCH = 512
+IE_MAX_BATCH = 768
 
 
 class ie_config(C.Structure):

@@ -86,7 +86,9 @@ struct ie_encoder {
   ie_config cfg{};
   int num_sms = 148;
   int e_pad = 0;  // emb_sz rounded up to 64
-  std::vector<Layer> layers;
+  std::vector<Layer> layers;   // plan A: u ~ out/148 units per CTA (N = 160 pair tiles at H = 2400): B <= 512
+  std::vector<Layer> layersB;  // plan B: u = 32 (N = 256 pair tiles): three batches per launch (512 < B <= 768)
+  int use_wide = 1, wide_checked = 0;
   DevBuf emb;  // bf16 [vocab, e_pad]
   bool emb_loaded = false;
   // workspace
@@ -125,19 +127,20 @@ struct ie_mlp {
 
 namespace {
 
-int plan_layers(ie_encoder* h) {
+int plan_layers(ie_encoder* h, std::vector<Layer>& layers, int u_fixed) {
   const ie_config& c = h->cfg;
   h->e_pad = static_cast<int>(round_up(c.emb_sz, 64));
-  h->layers.resize(c.n_layers);
+  layers.resize(c.n_layers);
   int prev_pad = h->e_pad;
   for (int l = 0; l < c.n_layers; ++l) {
-    Layer& L = h->layers[l];
+    Layer& L = layers[l];
     L.in = (l == 0) ? c.emb_sz : c.n_hid;
     L.out = (l == c.n_layers - 1) ? c.emb_sz : c.n_hid;
     // u hidden units per CTA: multiple of 4, as many CTAs as fit on the SMs (one wave)
-    L.u = 4 * static_cast<int>((L.out + 4ll * h->num_sms - 1) / (4ll * h->num_sms));
+    L.u = u_fixed > 0 ? u_fixed : 4 * static_cast<int>((L.out + 4ll * h->num_sms - 1) / (4ll * h->num_sms));
     if (L.u > 32) return fail(IE_ERR_INVALID, "hidden size %d too large for %d SMs", L.out, h->num_sms);
     L.n_cta = (L.out + L.u - 1) / L.u;
+    if (u_fixed > 0 && (L.n_cta & 1)) ++L.n_cta;  // CTA pairs: the last pair's second slice is pure padding
     L.out_pad = L.n_cta * L.u;
     L.kin_pad = prev_pad;
     L.kh_pad = static_cast<int>(round_up(L.out_pad, 64));
@@ -189,10 +192,11 @@ int upload_sliced(const float* host, int rows_src, int cols, const std::vector<i
 int ensure_workspace(ie_encoder* h, int b_pad, int T, bool want_raw) {
   const ie_config& c = h->cfg;
   long long max_out_pad = 0, max_kh = 0;
-  for (const Layer& L : h->layers) {
-    max_out_pad = std::max<long long>(max_out_pad, L.out_pad);
-    max_kh = std::max<long long>(max_kh, L.kh_pad);
-  }
+  for (const std::vector<Layer>* plan : {&h->layers, &h->layersB})
+    for (const Layer& L : *plan) {
+      max_out_pad = std::max<long long>(max_out_pad, L.out_pad);
+      max_kh = std::max<long long>(max_kh, L.kh_pad);
+    }
   const long long rows = static_cast<long long>(T) * b_pad;
   CK(h->ids.reserve(static_cast<size_t>(IE_MAX_BATCH) * T * sizeof(int64_t)));
   CK(h->lengths.reserve(IE_MAX_BATCH * sizeof(int)));
@@ -209,8 +213,8 @@ int ensure_workspace(ie_encoder* h, int b_pad, int T, bool want_raw) {
   CK(h->pool_max.reserve(pb));
   CK(h->pool_last.reserve(pb));
   CK(h->out.reserve(static_cast<size_t>(IE_MAX_BATCH) * 3 * c.emb_sz * sizeof(float)));
-  if (want_raw) CK(h->raw.reserve(static_cast<size_t>(b_pad) * T * h->layers.back().out_pad * sizeof(float)));
-  CK(h->step_done.reserve(static_cast<size_t>(c.n_layers) * T * 2 * sizeof(unsigned)));
+  if (want_raw) CK(h->raw.reserve(static_cast<size_t>(b_pad) * T * max_out_pad * sizeof(float)));
+  CK(h->step_done.reserve(static_cast<size_t>(c.n_layers) * T * 3 * sizeof(unsigned)));
   return IE_OK;
 }
 
@@ -231,12 +235,16 @@ int run_encoder(ie_encoder* h, const int64_t* ids, const int32_t* lengths, int B
   if (!h->emb_loaded) return fail(IE_ERR_STATE, "embedding not loaded");
   for (const Layer& L : h->layers)
     if (!L.loaded) return fail(IE_ERR_STATE, "LSTM layer weights not loaded");
+  for (const Layer& L : h->layersB)
+    if (!L.loaded) return fail(IE_ERR_STATE, "LSTM layer weights not loaded");
   if (B < 1 || B > IE_MAX_BATCH) return fail(IE_ERR_INVALID, "B=%d outside [1,%d]", B, IE_MAX_BATCH);
   if (T < 1) return fail(IE_ERR_INVALID, "T=%d must be >= 1", T);
   if (ids == nullptr || (out == nullptr && raw_out == nullptr)) return fail(IE_ERR_INVALID, "null pointer");
   const bool dev = (flags & IE_FLAG_DEVICE_PTRS) != 0;
   const bool pooled = out != nullptr;
-  const int b_pad = B <= 128 ? 128 : (B <= 256 ? 256 : 512);
+  const int b_pad = B <= 128 ? 128 : (B <= 256 ? 256 : (B <= 512 ? 512 : 768));
+  const bool wide = (b_pad == 768);
+  std::vector<Layer>& LS = wide ? h->layersB : h->layers;
   // workspace cap (tokens per call); IE_MAX_TOKENS lowers it, e.g. to exercise the caller's batch-halving loop
   long long cap = 1ll << 21;
   if (const char* e = getenv("IE_MAX_TOKENS")) cap = std::max(128ll, atoll(e));
@@ -280,7 +288,20 @@ int run_encoder(ie_encoder* h, const int64_t* ids, const int32_t* lengths, int B
 
   const long long rows = static_cast<long long>(T) * b_pad;
   // persistent per-layer recurrent kernel: needs both 128-row halves and every CTA of a layer co-resident
-  bool seq = h->use_seq && b_pad >= 256;
+  bool seq = h->use_seq && b_pad >= 256 && !wide;
+  if (wide) {
+    if (h->use_wide && !h->wide_checked) {
+      for (const Layer& L : h->layersB) {
+        ie::LstmWideArgs q{};
+        q.T = 1; q.ng = 3; q.u = L.u; q.n_cta = L.n_cta; q.out_pad = L.out_pad; q.kh_pad = L.kh_pad;
+        q.num_sms = h->num_sms; q.check_only = 1;
+        if (ie::launch_lstm_wide(q, s) != cudaSuccess) h->use_wide = 0;
+      }
+      cudaGetLastError();
+      h->wide_checked = 1;
+    }
+    if (!h->use_wide) return fail(IE_ERR_STATE, "B > 512 needs the wide persistent kernel (caller splits the batch)");
+  }
   if (seq && !h->seq_checked) {
     for (const Layer& L : h->layers) {
       ie::LstmSeqArgs q{};
@@ -292,7 +313,7 @@ int run_encoder(ie_encoder* h, const int64_t* ids, const int32_t* lengths, int B
     h->seq_checked = 1;
   }
   if (b_pad == 512 && !seq) return fail(IE_ERR_STATE, "B > 256 needs the persistent kernel (caller splits the batch)");
-  if (seq) CK(cudaMemsetAsync(h->step_done.p, 0, static_cast<size_t>(c.n_layers) * T * 2 * sizeof(unsigned), s));
+  if (seq || wide) CK(cudaMemsetAsync(h->step_done.p, 0, static_cast<size_t>(c.n_layers) * T * 3 * sizeof(unsigned), s));
   // slot 0 of both hidden-state rings is h_{-1} = 0; a previous call with another B_pad may have written these rows
   for (int i = 0; i < 2; ++i)
     CK(cudaMemsetAsync(h->y[i].p, 0, static_cast<size_t>(b_pad) * h->y_ld * sizeof(__nv_bfloat16), s));
@@ -300,7 +321,7 @@ int run_encoder(ie_encoder* h, const int64_t* ids, const int32_t* lengths, int B
   const __nv_bfloat16* layer_in = h->x0.as<__nv_bfloat16>();
   long long layer_in_ld = h->e_pad;
   for (int l = 0; l < c.n_layers; ++l) {
-    Layer& L = h->layers[l];
+    Layer& L = LS[l];
     const bool last = (l == c.n_layers - 1);
     // hoisted input projection over all T*b_pad rows
     ie::GemmArgs g{};
@@ -349,11 +370,20 @@ int run_encoder(ie_encoder* h, const int64_t* ids, const int32_t* lengths, int B
     a.kh_pad = L.kh_pad;
     a.ldy = h->y_ld;
     a.raw_ld = L.out_pad;
-    if (seq) {
+    if (wide) {
+      ie::LstmWideArgs q{};
+      q.tm_h = a.tm_h; q.tm_w = a.tm_w; q.gx = a.gx; q.c = a.c; q.y = a.y; q.raw = a.raw;
+      q.pool_sum = a.pool_sum; q.pool_max = a.pool_max; q.pool_last = a.pool_last; q.lengths = a.lengths;
+      q.step_done = h->step_done.as<unsigned>() + static_cast<size_t>(l) * T * 3;
+      q.T = T; q.ng = 3; q.u = L.u; q.n_cta = L.n_cta; q.out_pad = L.out_pad; q.kh_pad = L.kh_pad;
+      q.ldy = a.ldy; q.raw_ld = a.raw_ld; q.fast_math = h->fast_math; q.num_sms = h->num_sms; q.check_only = 0;
+      CK(ie::launch_lstm_wide(q, s));
+      h->launches += 1;
+    } else if (seq) {
       ie::LstmSeqArgs q{};
       q.tm_h = a.tm_h; q.tm_w = a.tm_w; q.gx = a.gx; q.y = a.y; q.raw = a.raw;
       q.pool_sum = a.pool_sum; q.pool_max = a.pool_max; q.pool_last = a.pool_last; q.lengths = a.lengths;
-      q.step_done = h->step_done.as<unsigned>() + static_cast<size_t>(l) * T * 2;
+      q.step_done = h->step_done.as<unsigned>() + static_cast<size_t>(l) * T * 3;
       q.T = T; q.b_pad = b_pad; q.u = L.u; q.n_cta = L.n_cta; q.out_pad = L.out_pad; q.kh_pad = L.kh_pad;
       q.ldy = a.ldy; q.raw_ld = a.raw_ld; q.check_only = 0;
       q.fast_math = h->fast_math;
@@ -379,7 +409,7 @@ int run_encoder(ie_encoder* h, const int64_t* ids, const int32_t* lengths, int B
     cur ^= 1;
   }
 
-  const Layer& LL = h->layers.back();
+  const Layer& LL = LS.back();
   if (pooled) {
     float* out_dev = dev ? out : h->out.as<float>();
     CK(ie::launch_pool_finalize(h->pool_sum.as<float>(), h->pool_max.as<float>(), h->pool_last.as<float>(),
@@ -437,7 +467,8 @@ int ie_encoder_create(const ie_config* cfg, ie_encoder** out) {
   if (const char* e = getenv("IE_SEQ")) h->use_seq = atoi(e);
   h->fast_math = (cfg->flags & IE_CFG_ACCURATE_GATES) ? 0 : 1;
   if (const char* e = getenv("IE_FAST_MATH")) h->fast_math = atoi(e);
-  int rc = plan_layers(h);
+  int rc = plan_layers(h, h->layers, 0);
+  if (rc == IE_OK) rc = plan_layers(h, h->layersB, 32);
   if (rc != IE_OK) { delete h; return rc; }
   e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) { delete h; return cuda_fail(e, "cudaStreamCreate"); }
@@ -450,6 +481,7 @@ void ie_encoder_destroy(ie_encoder* h) {
   cudaSetDevice(h->cfg.device);
   cudaDeviceSynchronize();
   for (Layer& L : h->layers) { L.w_ih.release(); L.w_hh.release(); L.bias.release(); }
+  for (Layer& L : h->layersB) { L.w_ih.release(); L.w_hh.release(); L.bias.release(); }
   DevBuf* bufs[] = {&h->emb, &h->ids, &h->lengths, &h->x0, &h->y[0], &h->y[1], &h->gx, &h->c, &h->pool_sum,
                     &h->pool_max, &h->pool_last, &h->out, &h->raw, &h->err, &h->step_done, &h->trace};
   for (DevBuf* b : bufs) b->release();
@@ -477,41 +509,58 @@ int ie_encoder_load_layer(ie_encoder* h, int32_t layer, const float* w_ih, const
   if (layer < 0 || layer >= h->cfg.n_layers) return fail(IE_ERR_INVALID, "layer %d out of range", layer);
   std::lock_guard<std::mutex> lk(h->mu);
   CK(cudaSetDevice(h->cfg.device));
-  Layer& L = h->layers[layer];
-  const std::vector<int> perm = slice_perm(L);
-  int rc = upload_sliced(w_ih, 4 * L.out, L.in, perm, L.kin_pad, L.w_ih, h->own_stream);
-  if (rc != IE_OK) return rc;
-  rc = upload_sliced(w_hh, 4 * L.out, L.out, perm, L.kh_pad, L.w_hh, h->own_stream);
-  if (rc != IE_OK) return rc;
-  std::vector<float> bias(perm.size());
-  for (size_t r = 0; r < perm.size(); ++r) bias[r] = perm[r] < 0 ? 0.0f : b_ih[perm[r]] + b_hh[perm[r]];
-  CK(L.bias.reserve(bias.size() * sizeof(float)));
-  CK(cudaMemcpy(L.bias.p, bias.data(), bias.size() * sizeof(float), cudaMemcpyHostToDevice));
-  L.loaded = true;
+  for (std::vector<Layer>* plan : {&h->layers, &h->layersB}) {  // both weight layouts stay resident (2 x 266 MB at R4)
+    Layer& L = (*plan)[layer];
+    const std::vector<int> perm = slice_perm(L);
+    int rc = upload_sliced(w_ih, 4 * L.out, L.in, perm, L.kin_pad, L.w_ih, h->own_stream);
+    if (rc != IE_OK) return rc;
+    rc = upload_sliced(w_hh, 4 * L.out, L.out, perm, L.kh_pad, L.w_hh, h->own_stream);
+    if (rc != IE_OK) return rc;
+    std::vector<float> bias(perm.size());
+    for (size_t r = 0; r < perm.size(); ++r) bias[r] = perm[r] < 0 ? 0.0f : b_ih[perm[r]] + b_hh[perm[r]];
+    CK(L.bias.reserve(bias.size() * sizeof(float)));
+    CK(cudaMemcpy(L.bias.p, bias.data(), bias.size() * sizeof(float), cudaMemcpyHostToDevice));
+    L.loaded = true;
+  }
   return IE_OK;
+}
+
+// rows beyond what the available persistent kernels take in one launch are run as consecutive sub-batches
+static int encode_locked(ie_encoder* h, const int64_t* ids, const int32_t* lengths, int B, int T, float* out, int flags,
+                         cudaStream_t s) {
+  const long long ow = 3ll * h->cfg.emb_sz;
+  if (B > 512) {
+    if (h->use_wide) {
+      const int rc = run_encoder(h, ids, lengths, B, T, out, nullptr, flags, s);
+      if (rc != IE_ERR_STATE || h->use_wide) return rc;
+    }
+    const int rc = encode_locked(h, ids, lengths, 512, T, out, flags, s);
+    if (rc != IE_OK) return rc;
+    return encode_locked(h, ids + 512ll * T, lengths + 512, B - 512, T, out + 512 * ow, flags, s);
+  }
+  if (B > 256) {
+    if (h->use_seq) {
+      const int rc = run_encoder(h, ids, lengths, B, T, out, nullptr, flags, s);
+      if (rc != IE_ERR_STATE || h->use_seq) return rc;
+    }
+    const int rc = encode_locked(h, ids, lengths, 256, T, out, flags, s);
+    if (rc != IE_OK) return rc;
+    return encode_locked(h, ids + 256ll * T, lengths + 256, B - 256, T, out + 256 * ow, flags, s);
+  }
+  return run_encoder(h, ids, lengths, B, T, out, nullptr, flags, s);
 }
 
 int ie_encoder_encode(ie_encoder* h, const int64_t* ids, const int32_t* lengths, int32_t B, int32_t T, float* out,
                       int32_t flags, void* stream) {
   if (h == nullptr) return fail(IE_ERR_INVALID, "null handle");
   if (out == nullptr) return fail(IE_ERR_INVALID, "out is null");
+  if (ids == nullptr || lengths == nullptr) return fail(IE_ERR_INVALID, "null pointer");
+  if (B < 1 || B > IE_MAX_BATCH) return fail(IE_ERR_INVALID, "B=%d outside [1,%d]", B, IE_MAX_BATCH);
   std::lock_guard<std::mutex> lk(h->mu);
   // device-pointer mode: `stream` is used verbatim (NULL = the legacy default stream, e.g. torch's default);
   // host-pointer mode: NULL selects the handle's own stream
   cudaStream_t s = (stream || (flags & IE_FLAG_DEVICE_PTRS)) ? static_cast<cudaStream_t>(stream) : h->own_stream;
-  if (B > 256 && B <= IE_MAX_BATCH && (!h->use_seq)) {
-    // without the persistent kernel the two 256-row batches are simply run one after the other
-    int rc = run_encoder(h, ids, lengths, 256, T, out, nullptr, flags, s);
-    if (rc != IE_OK) return rc;
-    return run_encoder(h, ids + 256ll * T, lengths + 256, B - 256, T, out + 256ll * 3 * h->cfg.emb_sz, nullptr, flags, s);
-  }
-  int rc = run_encoder(h, ids, lengths, B, T, out, nullptr, flags, s);
-  if (rc == IE_ERR_STATE && B > 256 && !h->use_seq) {  // the co-residency check just turned the persistent kernel off
-    rc = run_encoder(h, ids, lengths, 256, T, out, nullptr, flags, s);
-    if (rc != IE_OK) return rc;
-    return run_encoder(h, ids + 256ll * T, lengths + 256, B - 256, T, out + 256ll * 3 * h->cfg.emb_sz, nullptr, flags, s);
-  }
-  return rc;
+  return encode_locked(h, ids, lengths, B, T, out, flags, s);
 }
 
 int ie_encoder_raw_features(ie_encoder* h, const int64_t* ids, int32_t B, int32_t T, float* raw, int32_t flags,

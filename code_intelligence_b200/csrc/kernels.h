@@ -76,6 +76,25 @@ struct LstmSeqArgs {
 };
 cudaError_t launch_lstm_seq(const LstmSeqArgs& a, cudaStream_t stream);
 
+// ---- persistent recurrent layer, wide tiles (lstm_wide.cu): N = 256 per CTA pair, up to 3 batches per launch -------
+struct LstmWideArgs {
+  CUtensorMap tm_h;  // hidden-state slots  [(T+1)*256*ng rows, kh_pad], box {64, 128}
+  CUtensorMap tm_w;  // sliced W_hh (u = 32) [4*out_pad rows, kh_pad], box {64, 128}
+  const float* gx;
+  float* c;          // [256*ng, out_pad] cell state
+  __nv_bfloat16* y;
+  float* raw;
+  float* pool_sum;
+  float* pool_max;
+  float* pool_last;
+  const int* lengths;
+  unsigned* step_done;  // [T*ng] zero-initialised
+  int T, ng, u, n_cta, out_pad, kh_pad;
+  long long ldy, raw_ld;
+  int fast_math, num_sms, check_only;
+};
+cudaError_t launch_lstm_wide(const LstmWideArgs& a, cudaStream_t stream);
+
 // ---- UMMA issue/throughput micro-benchmark (umma_bench.cu, debug) ------------------------------------------------
 cudaError_t run_umma_rate(int mode, int n, int iters, int commit_every, int grid, int ntiles, long long* host_out);
 

@@ -40,8 +40,9 @@ extern "C" {
 #define IE_CFG_ACCURATE_GATES 1 /* ex2+rcp sigmoid/tanh (abs err ~1e-7) instead of the default single-MUFU          */
                                 /* tanh.approx.f32 gates (rel err 2^-11; no measurable effect on the parity metrics) */
 
-#define IE_MAX_BATCH 512 /* rows per ie_encoder_encode call: up to two 256-row batches ride one launch (each a CTA-pair
-                            M=256 UMMA tile); they share the kernel, not their results */
+#define IE_MAX_BATCH 768 /* rows per ie_encoder_encode call: up to three independent 256-row batches ride one launch of
+                            the persistent recurrent kernel (each a CTA-pair M=256 UMMA tile); they share the kernel,
+                            not their results */
 
 typedef struct ie_encoder ie_encoder;
 typedef struct ie_mlp ie_mlp;

@@ -105,6 +105,12 @@ def check_dual():
     return [_enc_parity(3, 96, 200, 500, 300, 19, min_len=1), _enc_parity(4, 800, 2400, 60000, 512, 64, min_len=8)]
 
 
+def check_wide():
+    # 512 < B <= 768: three batches per launch, N = 256 pair tiles (lstm_wide.cu)
+    return [_enc_parity(3, 96, 200, 500, 700, 19, min_len=1), _enc_parity(4, 800, 2400, 60000, 768, 64, min_len=8),
+            _enc_parity(3, 800, 2400, 60000, 600, 40, min_len=4, scale=3.0)]
+
+
 def check_speed():
     """B=256, T=512 R4 with device-resident inputs: per-encode CUDA-event time."""
     import numpy as np
@@ -136,7 +142,7 @@ def check_speed():
     return out
 
 
-CHECKS = dict(gemm=check_gemm, tiny=check_tiny, r4_small=check_r4_small, n3=check_n3, n3b=check_n3b, dual=check_dual, speed=check_speed)
+CHECKS = dict(gemm=check_gemm, tiny=check_tiny, r4_small=check_r4_small, n3=check_n3, n3b=check_n3b, dual=check_dual, wide=check_wide, speed=check_speed)
 
 if __name__ == '__main__':
     ap = argparse.ArgumentParser()
