@@ -377,6 +377,14 @@ int run_encoder(ie_encoder* h, const int64_t* ids, const int32_t* lengths, int B
       q.step_done = h->step_done.as<unsigned>() + static_cast<size_t>(l) * T * 3;
       q.T = T; q.ng = 3; q.u = L.u; q.n_cta = L.n_cta; q.out_pad = L.out_pad; q.kh_pad = L.kh_pad;
       q.ldy = a.ldy; q.raw_ld = a.raw_ld; q.fast_math = h->fast_math; q.num_sms = h->num_sms; q.check_only = 0;
+      q.trace = nullptr;
+      if (l == h->trace_layer) {
+        const int grid = 2 * std::min(h->num_sms / 2, 3 * (L.n_cta / 2));
+        CK(h->trace.reserve(static_cast<size_t>(grid) * T * 12 * sizeof(long long), true));
+        q.trace = h->trace.as<long long>();
+        h->trace_T = T;
+        h->trace_ctas = grid;
+      }
       CK(ie::launch_lstm_wide(q, s));
       h->launches += 1;
     } else if (seq) {

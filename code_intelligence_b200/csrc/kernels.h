@@ -92,6 +92,7 @@ struct LstmWideArgs {
   int T, ng, u, n_cta, out_pad, kh_pad;
   long long ldy, raw_ld;
   int fast_math, num_sms, check_only;
+  long long* trace;  // optional [grid][T][12] timeline (debug)
 };
 cudaError_t launch_lstm_wide(const LstmWideArgs& a, cudaStream_t stream);
 

@@ -35,7 +35,8 @@ lstm_wide_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant
                  const float* __restrict__ gx, float* __restrict__ cstate, __nv_bfloat16* __restrict__ y,
                  float* __restrict__ raw, float* __restrict__ pool_sum, float* __restrict__ pool_max,
                  float* __restrict__ pool_last, const int* __restrict__ lengths, unsigned* __restrict__ step_done, int T,
-                 int ng, int tiles, int out_pad, int num_k_blocks, long long ldy, long long raw_ld, int fast_math) {
+                 int ng, int tiles, int out_pad, int num_k_blocks, long long ldy, long long raw_ld, int fast_math,
+                 long long* __restrict__ trace) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t rawaddr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (rawaddr & 1023u)) & 1023u);
@@ -54,6 +55,10 @@ lstm_wide_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // optional timeline of the pair's FIRST chain: [cta][t][12] (%globaltimer ns; slots 8-10 SM cycles); null in production
+#define IE_TRACE(slot, tt) do { if (trace) { unsigned long long _g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_g)); \
+    trace[(static_cast<long long>(blockIdx.x) * T + (tt)) * 12 + (slot)] = static_cast<long long>(_g); } } while (0)
+#define IE_TRACE_VAL(slot, tt, v) do { if (trace) trace[(static_cast<long long>(blockIdx.x) * T + (tt)) * 12 + (slot)] = (v); } while (0)
   const uint32_t crank = cluster_ctarank();
   const int pair = blockIdx.x >> 1;
   const int P = static_cast<int>(gridDim.x >> 1);
@@ -98,6 +103,7 @@ lstm_wide_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant
             wait_flag_ge_relaxed(step_done + (t - 1) * ng + g, batch_ctas);
             fence_proxy_async();
           }
+          if (ci == 0) IE_TRACE(0, t);
           const int row0 = t * b_pad + g * 256 + static_cast<int>(crank) * 128;
           for (int kb0 = 0; kb0 < num_k_blocks; kb0 += kWGA) {
             const int n = min(kWGA, num_k_blocks - kb0);
@@ -109,6 +115,7 @@ lstm_wide_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant
                                kEvictNormal);
             if (++stage == kWAStages) { stage = 0; phase ^= 1; }
           }
+          if (ci == 0) IE_TRACE(1, t);
         }
       }
     }
@@ -145,10 +152,20 @@ lstm_wide_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant
       for (int t = 0; t < T; ++t) {
         for (int ci = 0; ci < my_chains; ++ci) {
           const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(ci * kTileN);
+          long long wa = 0, ww = 0, t_first = 0;
           for (int kb = 0; kb < num_k_blocks; ++kb) {
             const int ja = kb % kWGA, jw = kb % kWGW;
-            if (ja == 0) mbar_wait(&afull[as], aph);
-            if (jw == 0) mbar_wait(&wfull[ws], wph);
+            if (ja == 0) {
+              const long long c0 = trace ? clock64() : 0;
+              mbar_wait(&afull[as], aph);
+              if (kb == 0) { if (ci == 0) IE_TRACE(2, t); t_first = trace ? clock64() : 0; }
+              else if (trace) wa += clock64() - c0;
+            }
+            if (jw == 0) {
+              const long long c0 = trace ? clock64() : 0;
+              mbar_wait(&wfull[ws], wph);
+              if (trace) ww += clock64() - c0;
+            }
             tc_fence_after();
             const uint64_t da = umma_desc_sw128(a_base + (as * kWGA + ja) * a_bytes);
             const uint64_t db = umma_desc_sw128(w_base + (ws * kWGW + jw) * w_bytes);
@@ -165,6 +182,12 @@ lstm_wide_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant
             }
           }
           umma_commit_pair_mc(&tfull[ci], 0x3);
+          if (ci == 0) {
+            IE_TRACE(3, t);
+            IE_TRACE_VAL(8, t, wa);
+            IE_TRACE_VAL(9, t, ww);
+            IE_TRACE_VAL(10, t, trace ? clock64() - t_first : 0);
+          }
         }
       }
     }
@@ -198,8 +221,10 @@ lstm_wide_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant
 #pragma unroll
           for (int i = 0; i < 4; ++i) prefetch_l2(nx + i * 128);
         }
+        if (threadIdx.x == 128 && ci == 0) IE_TRACE(7, t);
         mbar_wait(&tfull[ci], static_cast<uint32_t>(t & 1));
         tc_fence_after();
+        if (threadIdx.x == 128 && ci == 0) IE_TRACE(4, t);
 #pragma unroll 1
         for (int ch = 0; ch < 8; ++ch) {
           if (ch + 1 < 8) {  // next chunk's Gx / c in flight while this one is computed
@@ -256,11 +281,13 @@ lstm_wide_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant
           cc = cn4;
         }
         // publish (step t, batch g): accumulator drained, h_t visible
+        if (threadIdx.x == 128 && ci == 0) IE_TRACE(5, t);
         tc_fence_before();
         named_bar_sync(1, 256);
         if (threadIdx.x == 128) {
           __threadfence();
           red_relaxed_add(step_done + t * ng + g, 1u);
+          if (ci == 0) IE_TRACE(6, t);
         }
       }
     }
@@ -310,7 +337,7 @@ cudaError_t launch_lstm_wide(const LstmWideArgs& a, cudaStream_t stream) {
   }
   lstm_wide_kernel<<<2 * pairs, kWThreads, smem, stream>>>(a.tm_h, a.tm_w, a.gx, a.c, a.y, a.raw, a.pool_sum, a.pool_max,
                                                           a.pool_last, a.lengths, a.step_done, a.T, a.ng, tiles, a.out_pad,
-                                                          a.kh_pad / 64, a.ldy, a.raw_ld, a.fast_math);
+                                                          a.kh_pad / 64, a.ldy, a.raw_ld, a.fast_math, a.trace);
   return cudaGetLastError();
 }
 

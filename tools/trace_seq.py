@@ -23,7 +23,7 @@ ids = torch.randint(2, 60000, (a.B, a.T), generator=g, dtype=torch.int64).numpy(
 enc.encode_ids(ids)   # warm
 enc._lib.ie_debug_seq_trace(enc._h, a.layer, None, 0)
 enc.encode_ids(ids)
-n_cta = 120 if a.layer < 3 else 100
+n_cta = (120 if a.layer < 3 else 100) if a.B <= 512 else (148 if a.layer < 3 else 78)
 buf = np.zeros((n_cta, a.T, 12), dtype=np.int64)
 n = enc._lib.ie_debug_seq_trace(enc._h, -1, buf.ctypes.data, buf.size)
 print("records", n)
@@ -47,7 +47,7 @@ print("global: MMA thread per step (us @%.2f GHz): waiting for h stages %.2f, wa
 mm = (tr_all[::2, :, 3] - tr_all[::2, :, 2])[:, sel].mean(1)
 print("global: MMA phase (first A landed -> last commit) us: mean", mm.mean() * us, "max", mm.max() * us)
 names = ["0 barrier passed", "1 last A issued", "2 first A landed(MMA)", "3 MMAs issued+commit", "4 tfull seen", "5 epilogue stores done", "6 fenced+bar", "7 gx loads issued"]
-for cta in (0, 1, 2, 59, 119 if n_cta == 120 else 99):
+for cta in (0, 2, 4, 80, n_cta - 2):
     tr = buf[cta].astype(np.float64)
     # per step, relative to slot 0 (barrier passed) of the same step; leader CTAs have MMA slots
     rel = (tr - tr[:, 0:1]) * us
