@@ -210,12 +210,17 @@ lstm_wide_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant
         float4* cp = reinterpret_cast<float4*>(cstate + static_cast<long long>(brow) * out_pad + unit0);
         __nv_bfloat16* yrow = y + (static_cast<long long>(t + 1) * b_pad + brow) * ldy + unit0;
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(ci * kTileN + half * 128);
-        // chunk 0 operands while the MMAs still run
-        float4 gq[4], gn[4];
-        float4 cc, cn4;
+        // Gx and c of the first kPF chunks are loaded while the MMAs still run; the loads of chunk ch + kPF are
+        // issued right after chunk ch has been computed (the loop is fully unrolled: at most kPF chunks are live)
+        constexpr int kPF = 4;
+        float4 gxr[8][4];
+        float4 cr[8];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) gq[i] = __ldg(gxp + i);
-        cc = (t == 0) ? make_float4(0.f, 0.f, 0.f, 0.f) : cp[0];
+        for (int ch = 0; ch < kPF; ++ch) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) gxr[ch][i] = __ldg(gxp + ch * 4 + i);
+          cr[ch] = (t == 0) ? make_float4(0.f, 0.f, 0.f, 0.f) : cp[ch];
+        }
         if (t + 1 < T) {
           const char* nx = reinterpret_cast<const char*>(gxp) + static_cast<long long>(b_pad) * out_pad * 16ll;
 #pragma unroll
@@ -225,25 +230,20 @@ lstm_wide_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant
         mbar_wait(&tfull[ci], static_cast<uint32_t>(t & 1));
         tc_fence_after();
         if (threadIdx.x == 128 && ci == 0) IE_TRACE(4, t);
-#pragma unroll 1
-        for (int ch = 0; ch < 8; ++ch) {
-          if (ch + 1 < 8) {  // next chunk's Gx / c in flight while this one is computed
 #pragma unroll
-            for (int i = 0; i < 4; ++i) gn[i] = __ldg(gxp + (ch + 1) * 4 + i);
-            cn4 = (t == 0) ? make_float4(0.f, 0.f, 0.f, 0.f) : cp[ch + 1];
-          }
+        for (int ch = 0; ch < 8; ++ch) {
           uint32_t r[16];
           __syncwarp();
           tmem_ld16(taddr + ch * 16, r);
           tmem_ld_wait();
-          const float cprev[4] = {cc.x, cc.y, cc.z, cc.w};
+          const float cprev[4] = {cr[ch].x, cr[ch].y, cr[ch].z, cr[ch].w};
           float cnew[4], hn[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            const float zi = __uint_as_float(r[4 * u + 0]) + gq[u].x;
-            const float zf = __uint_as_float(r[4 * u + 1]) + gq[u].y;
-            const float zg = __uint_as_float(r[4 * u + 2]) + gq[u].z;
-            const float zo = __uint_as_float(r[4 * u + 3]) + gq[u].w;
+            const float zi = __uint_as_float(r[4 * u + 0]) + gxr[ch][u].x;
+            const float zf = __uint_as_float(r[4 * u + 1]) + gxr[ch][u].y;
+            const float zg = __uint_as_float(r[4 * u + 2]) + gxr[ch][u].z;
+            const float zo = __uint_as_float(r[4 * u + 3]) + gxr[ch][u].w;
             if (fast_math) {
               cnew[u] = sigmoid_fast(zf) * cprev[u] + sigmoid_fast(zi) * tanh_fast(zg);
               hn[u] = sigmoid_fast(zo) * tanh_fast(cnew[u]);
@@ -251,6 +251,11 @@ lstm_wide_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant
               cnew[u] = sigmoid_acc(zf) * cprev[u] + sigmoid_acc(zi) * tanh_acc(zg);
               hn[u] = sigmoid_acc(zo) * tanh_acc(cnew[u]);
             }
+          }
+          if (ch + kPF < 8) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) gxr[ch + kPF][i] = __ldg(gxp + (ch + kPF) * 4 + i);
+            cr[ch + kPF] = (t == 0) ? make_float4(0.f, 0.f, 0.f, 0.f) : cp[ch + kPF];
           }
           cp[ch] = make_float4(cnew[0], cnew[1], cnew[2], cnew[3]);
           *reinterpret_cast<uint2*>(yrow + ch * 4) = make_uint2(pack_bf16x2(hn[0], hn[1]), pack_bf16x2(hn[2], hn[3]));
@@ -276,9 +281,6 @@ lstm_wide_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant
             *pm = m;
             if (t == len - 1) *reinterpret_cast<float4*>(pool_last + po) = make_float4(hn[0], hn[1], hn[2], hn[3]);
           }
-#pragma unroll
-          for (int i = 0; i < 4; ++i) gq[i] = gn[i];
-          cc = cn4;
         }
         // publish (step t, batch g): accumulator drained, h_t visible
         if (threadIdx.x == 128 && ci == 0) IE_TRACE(5, t);
