@@ -24,7 +24,7 @@ namespace ie {
 
 namespace {
 
-constexpr int kWThreads = 384;
+constexpr int kWThreads = 640;  // 4 role warps + 16 epilogue warps (4 per TMEM lane quarter, 64 columns each)
 constexpr int kWGA = 2, kWAStages = 3;  // h ring: 3 stages x 2 k-blocks x 16 KB
 constexpr int kWGW = 2, kWWStages = 3;  // W ring: 3 stages x 2 k-blocks x 16 KB
 constexpr int kTileN = 256;             // accumulator columns per tile = 64 hidden units
@@ -195,7 +195,7 @@ lstm_wide_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant
     // ---------------- epilogue ------------------------------------------------------------------------------
     const int e = warp - 4;
     const int q = e & 3;
-    const int half = e >> 2;  // which 128 of the tile's 256 columns
+    const int cq = e >> 2;  // which 64 of the tile's 256 columns (4 chunks of 16 = 16 hidden units per thread)
     const int row = static_cast<int>(crank) * 128 + q * 32 + lane;
     const bool pooled = pool_sum != nullptr;
     for (int t = 0; t < T; ++t) {
@@ -203,20 +203,19 @@ lstm_wide_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant
         const int c = pair + ci * P;
         const int g = c / tiles, j = c % tiles;
         const int brow = g * 256 + row;
-        const int unit0 = j * 64 + half * 32;
+        const int unit0 = j * 64 + cq * 16;
         const int len = pooled ? lengths[brow] : 1;
         const float4* gxp = reinterpret_cast<const float4*>(gx + (static_cast<long long>(t) * b_pad + brow) * (4ll * out_pad) +
                                                             4ll * unit0);
         float4* cp = reinterpret_cast<float4*>(cstate + static_cast<long long>(brow) * out_pad + unit0);
         __nv_bfloat16* yrow = y + (static_cast<long long>(t + 1) * b_pad + brow) * ldy + unit0;
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(ci * kTileN + half * 128);
-        // Gx and c of the first kPF chunks are loaded while the MMAs still run; the loads of chunk ch + kPF are
-        // issued right after chunk ch has been computed (the loop is fully unrolled: at most kPF chunks are live)
-        constexpr int kPF = 4;
-        float4 gxr[8][4];
-        float4 cr[8];
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(ci * kTileN + cq * 64);
+        // all of this thread's Gx (4 chunks x 4 units x 4 gates) and c are loaded while the MMAs still run
+        constexpr int kCh = 4;
+        float4 gxr[kCh][4];
+        float4 cr[kCh];
 #pragma unroll
-        for (int ch = 0; ch < kPF; ++ch) {
+        for (int ch = 0; ch < kCh; ++ch) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) gxr[ch][i] = __ldg(gxp + ch * 4 + i);
           cr[ch] = (t == 0) ? make_float4(0.f, 0.f, 0.f, 0.f) : cp[ch];
@@ -224,14 +223,14 @@ lstm_wide_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant
         if (t + 1 < T) {
           const char* nx = reinterpret_cast<const char*>(gxp) + static_cast<long long>(b_pad) * out_pad * 16ll;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) prefetch_l2(nx + i * 128);
+          for (int i = 0; i < 2; ++i) prefetch_l2(nx + i * 128);
         }
         if (threadIdx.x == 128 && ci == 0) IE_TRACE(7, t);
         mbar_wait(&tfull[ci], static_cast<uint32_t>(t & 1));
         tc_fence_after();
         if (threadIdx.x == 128 && ci == 0) IE_TRACE(4, t);
 #pragma unroll
-        for (int ch = 0; ch < 8; ++ch) {
+        for (int ch = 0; ch < kCh; ++ch) {
           uint32_t r[16];
           __syncwarp();
           tmem_ld16(taddr + ch * 16, r);
@@ -251,11 +250,6 @@ lstm_wide_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant
               cnew[u] = sigmoid_acc(zf) * cprev[u] + sigmoid_acc(zi) * tanh_acc(zg);
               hn[u] = sigmoid_acc(zo) * tanh_acc(cnew[u]);
             }
-          }
-          if (ch + kPF < 8) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) gxr[ch + kPF][i] = __ldg(gxp + (ch + kPF) * 4 + i);
-            cr[ch + kPF] = (t == 0) ? make_float4(0.f, 0.f, 0.f, 0.f) : cp[ch + kPF];
           }
           cp[ch] = make_float4(cnew[0], cnew[1], cnew[2], cnew[3]);
           *reinterpret_cast<uint2*>(yrow + ch * 4) = make_uint2(pack_bf16x2(hn[0], hn[1]), pack_bf16x2(hn[2], hn[3]));
@@ -285,7 +279,7 @@ lstm_wide_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant
         // publish (step t, batch g): accumulator drained, h_t visible
         if (threadIdx.x == 128 && ci == 0) IE_TRACE(5, t);
         tc_fence_before();
-        named_bar_sync(1, 256);
+        named_bar_sync(1, 512);
         if (threadIdx.x == 128) {
           __threadfence();
           red_relaxed_add(step_done + t * ng + g, 1u);
