@@ -302,7 +302,7 @@ int run_encoder(ie_encoder* h, const int64_t* ids, const int32_t* lengths, int B
     }
     if (!h->use_wide) return fail(IE_ERR_STATE, "B > 512 needs the wide persistent kernel (caller splits the batch)");
   }
-  if (seq && !h->seq_checked) {
+  if ((seq || wide) && !h->seq_checked) {
     for (const Layer& L : h->layers) {
       ie::LstmSeqArgs q{};
       q.T = 1; q.b_pad = 256; q.u = L.u; q.n_cta = L.n_cta; q.out_pad = L.out_pad; q.kh_pad = L.kh_pad;
@@ -320,9 +320,14 @@ int run_encoder(ie_encoder* h, const int64_t* ids, const int32_t* lengths, int B
   int cur = 0;
   const __nv_bfloat16* layer_in = h->x0.as<__nv_bfloat16>();
   long long layer_in_ld = h->e_pad;
+  // with three batches per launch the pooled last layer (narrow, latency bound) still runs the lstm_seq.cu kernel on its
+  // plan-A layout when that is possible; all other layers use the wide tiles of plan B
+  const Layer& lastA = h->layers.back();
+  const bool last_on_seq = wide && pooled && raw_out == nullptr && h->use_seq && lastA.u <= 12 && lastA.n_cta % 2 == 0 &&
+                           (c.n_layers < 2 || lastA.kin_pad == h->layersB[c.n_layers - 1].kin_pad);
   for (int l = 0; l < c.n_layers; ++l) {
-    Layer& L = LS[l];
     const bool last = (l == c.n_layers - 1);
+    Layer& L = (last && last_on_seq) ? h->layers[l] : LS[l];
     // hoisted input projection over all T*b_pad rows
     ie::GemmArgs g{};
     g.a = layer_in;
@@ -370,7 +375,7 @@ int run_encoder(ie_encoder* h, const int64_t* ids, const int32_t* lengths, int B
     a.kh_pad = L.kh_pad;
     a.ldy = h->y_ld;
     a.raw_ld = L.out_pad;
-    if (wide) {
+    if (wide && !(last && last_on_seq)) {
       ie::LstmWideArgs q{};
       q.tm_h = a.tm_h; q.tm_w = a.tm_w; q.gx = a.gx; q.c = a.c; q.y = a.y; q.raw = a.raw;
       q.pool_sum = a.pool_sum; q.pool_max = a.pool_max; q.pool_last = a.pool_last; q.lengths = a.lengths;
@@ -387,7 +392,7 @@ int run_encoder(ie_encoder* h, const int64_t* ids, const int32_t* lengths, int B
       }
       CK(ie::launch_lstm_wide(q, s));
       h->launches += 1;
-    } else if (seq) {
+    } else if (seq || (last && last_on_seq)) {
       ie::LstmSeqArgs q{};
       q.tm_h = a.tm_h; q.tm_w = a.tm_w; q.gx = a.gx; q.y = a.y; q.raw = a.raw;
       q.pool_sum = a.pool_sum; q.pool_max = a.pool_max; q.pool_last = a.pool_last; q.lengths = a.lengths;
@@ -417,7 +422,7 @@ int run_encoder(ie_encoder* h, const int64_t* ids, const int32_t* lengths, int B
     cur ^= 1;
   }
 
-  const Layer& LL = LS.back();
+  const Layer& LL = last_on_seq ? h->layers.back() : LS.back();
   if (pooled) {
     float* out_dev = dev ? out : h->out.as<float>();
     CK(ie::launch_pool_finalize(h->pool_sum.as<float>(), h->pool_max.as<float>(), h->pool_last.as<float>(),

@@ -376,8 +376,19 @@ cudaError_t launch_seq_t(const LstmSeqArgs& a, cudaStream_t stream) {
 
 // a.check_only != 0: only verify that the whole grid can be co-resident (no launch)
 cudaError_t launch_lstm_seq(const LstmSeqArgs& a, cudaStream_t stream) {
-  if (a.u % 4 || a.u < 4 || (a.b_pad != 256 && a.b_pad != 512) || a.kh_pad % 64 || a.n_cta % 2)
+  if (a.u % 4 || a.u < 4 || (a.b_pad != 256 && a.b_pad != 512 && a.b_pad != 768) || a.kh_pad % 64 || a.n_cta % 2)
     return cudaErrorInvalidValue;
+  if (a.b_pad == 768) {
+    // three batches per launch: only the narrow (<= 12 units per CTA) pooled last layer is run this way -- wider layers
+    // with three batches go through lstm_wide.cu
+    if (a.pool_sum == nullptr) return cudaErrorInvalidValue;
+    switch (a.u / 4) {
+      case 1: return launch_seq_t<1, 3, true>(a, stream);
+      case 2: return launch_seq_t<2, 3, true>(a, stream);
+      case 3: return launch_seq_t<3, 3, true>(a, stream);
+      default: return cudaErrorInvalidValue;
+    }
+  }
 #define IE_SEQ_CASE(n)                                                                                   \
   case n:                                                                                                \
     if (a.pool_sum != nullptr)                                                                           \
