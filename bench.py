@@ -7,10 +7,10 @@ One "step" = one pass of the hot path over one batch of 256 synthetic issues x 5
 shape; reference-deployed R4 encoder: L=4, E=800, H=2400, V=60000, random-init seed 1234): embedding gather, 4 hoisted
 input-projection GEMMs, 4 x 512 recurrent LSTM steps, masked [mean|max|last] pool -> (256, 2400) f32.
 
-Two consecutive steps (two batches of 256) ride one launch of the persistent recurrent kernel (ie_encoder_encode with 512
-rows = IE_MAX_BATCH): while one batch is in its epilogue / step barrier the tensor pipe works on the other.  Each step
-is still one batch of 256 issues with its own result rows; `single_batch` in the JSON line is the same measurement
-with one batch per launch.
+Three consecutive steps (three batches of 256) ride one launch of the persistent recurrent kernels (ie_encoder_encode with
+768 rows = IE_MAX_BATCH): the (batch, column-tile) MMA chains of the three batches are dealt over all 74 CTA pairs, and
+while one batch is in its epilogue / step barrier the tensor pipe works on another.  Each step is still one batch of
+256 issues with its own result rows; `single_batch` in the JSON line is the same measurement with one batch per launch.
 
 * `value`      : whole-job issues/s with the token ids already resident in HBM (CUDA events on the launching stream,
                  barrier + synchronize on both sides, max over ranks; under torchrun each rank encodes its own batches
@@ -181,7 +181,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=12)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -228,20 +228,26 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    # ---- launch plan: steps are submitted two at a time (2 x 256 rows per ie_encoder_encode call) -----------------
+    # ---- launch plan: steps are submitted kPerLaunch at a time (3 x 256 rows per ie_encoder_encode call) ----------
+    kPerLaunch = 3
     def plan(first, count, per_launch):
+        # a remainder launch (count % per_launch steps) goes first, so that the LAST launch of a region -- whose
+        # phase events feed the roofline -- is a full one
         out, i = [], first
+        r = count % per_launch
+        if r:
+            out.append((i, r))
+            i += r
         while i < first + count:
-            n = min(per_launch, first + count - i)
-            out.append((i, n))
-            i += n
+            out.append((i, per_launch))
+            i += per_launch
         return out
 
     ids_flat_dev = ids_dev.view((K + W) * B, T)
     ids_flat_np = ids_pin.view((K + W) * B, T).numpy()
-    len_dev2 = torch.full((2 * B,), T, dtype=torch.int32, device=dev)
-    len_host2 = np.full(2 * B, T, dtype=np.int32)
-    out_pin2 = torch.empty((2 * B, 3 * EMB), dtype=torch.float32).pin_memory()
+    len_dev2 = torch.full((kPerLaunch * B,), T, dtype=torch.int32, device=dev)
+    len_host2 = np.full(kPerLaunch * B, T, dtype=np.int32)
+    out_pin2 = torch.empty((kPerLaunch * B, 3 * EMB), dtype=torch.float32).pin_memory()
     out_np2 = out_pin2.numpy()
 
     def run_device(first, count, per_launch):
@@ -272,7 +278,7 @@ def main():
     ms_single, _, _ = device_arm(1)                  # one batch per launch (reported as `single_batch`)
     if rank == 0:
         sampler.start()
-    ms_max, launches, phases = device_arm(2)         # two batches per launch: the bulk-encode mode
+    ms_max, launches, phases = device_arm(kPerLaunch)  # three batches per launch: the bulk-encode mode
     value = world * B * K / (ms_max * 1e-3)
     single_value = world * B * K / (ms_single * 1e-3)
 
@@ -280,7 +286,7 @@ def main():
     lib, h = enc._lib, enc._h
     def run_host(first, count):
         chk = 0.0
-        for (i, n) in plan(first, count, 2):
+        for (i, n) in plan(first, count, kPerLaunch):
             rc = lib.ie_encoder_encode(h, ids_flat_np[i * B:(i + n) * B].ctypes.data, len_host2.ctypes.data, n * B, T,
                                        out_np2.ctypes.data, 0, None)
             assert rc == 0, lib.ie_last_error()
@@ -305,7 +311,7 @@ def main():
         # dominant kernel: the persistent recurrent kernel of the 2400-wide layers (one launch = all T steps of one
         # layer for the batches riding the launch): avg launch duration from the CUDA events recorded around it inside
         # ie_encoder_encode, last timed launch
-        batches = 2 if K >= 2 else 1
+        batches = kPerLaunch if K >= kPerLaunch else K   # batches riding the LAST timed launch (see plan())
         step_ms = phases["steps"][:N_LAYERS - 1]
         avg_launch_ms = sum(step_ms) / len(step_ms)
         flop_per_launch = STEP_FLOP_2400 * T * batches
@@ -322,7 +328,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": "configs[1]: 1M-issue bulk encode shape, fixed seq_len 512, batch 256 per step, "
                                    "R4 encoder (L=4,E=800,H=2400,V=60000) random-init seed 1234",
-                       "batch": B, "seq_len": T, "batches_per_launch": 2, "parallelism": f"dp{world} (issues sharded, one all-gather of outputs)",
+                       "batch": B, "seq_len": T, "batches_per_launch": kPerLaunch, "parallelism": f"dp{world} (issues sharded, one all-gather of outputs)",
                        "l2": "inputs larger than L2: each step streams ~6.5 GB of workspace (Gx 5 GB f32) and new ids",
                        "operands": "bf16 weights/activations, f32 accumulate, f32 cell state and pooling"},
             "clocks": clocks,
@@ -331,7 +337,8 @@ def main():
             "single_batch": {"value": single_value, "unit": "issues/s", "ms_per_step": ms_single / K,
                              "note": "same measurement with one batch of 256 per launch"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "tensor", "kernel": "lstm_seq_kernel<5,2> (persistent recurrent kernel, 2400-wide layers)",
+            "roofline": {"bound": "tensor", "kernel": "lstm_wide_kernel (persistent recurrent kernel, 2400-wide layers, "
+                                   "%d batches in the last timed launch)" % batches,
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "avg_launch_us": avg_launch_us,
                          "flop_per_launch": flop_per_launch,

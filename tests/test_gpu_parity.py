@@ -173,12 +173,13 @@ def test_edge_cases_and_errors(r4):
     want = R.encode_single(ref, np.array([2]))
     _assert_parity(one, want)
     np.testing.assert_allclose(one[0, :800], one[0, 800:1600])                 # mean == max == last for T=1
-    docs = R.synthetic_ids(600, 6, seed=3, min_len=2)                          # B > IE_MAX_BATCH (512) is sliced;
-    ids, lengths = _pad(docs)                                                  # 257..512 rows ride one launch
-    got = enc.encode_ids(ids, lengths)
-    np.testing.assert_array_equal(got[256], enc.encode_ids(ids[256:257], lengths[256:257])[0])
+    docs = R.synthetic_ids(900, 6, seed=3, min_len=2)                          # B > IE_MAX_BATCH (768) is sliced;
+    ids, lengths = _pad(docs)                                                  # 257..512 / 513..768 rows ride one launch
+    got = enc.encode_ids(ids, lengths)                                         # (three different kernel paths,
+    np.testing.assert_array_equal(got[256], enc.encode_ids(ids[256:257], lengths[256:257])[0])   # identical bits)
     np.testing.assert_array_equal(got[:257], enc.encode_ids(ids[:257], lengths[:257]))
-    np.testing.assert_array_equal(got[512:], enc.encode_ids(ids[512:], lengths[512:]))
+    np.testing.assert_array_equal(got[:600], enc.encode_ids(ids[:600], lengths[:600]))
+    np.testing.assert_array_equal(got[768:], enc.encode_ids(ids[768:], lengths[768:]))
     with pytest.raises(ValueError):
         enc.encode_ids(ids[:2], np.array([7, 1], dtype=np.int32))              # length > T
     with pytest.raises(ValueError):
@@ -208,6 +209,11 @@ def test_full_size_batch_properties(r4):
     b = enc.encode_ids(ids2, np.full(512, 512, dtype=np.int32))
     np.testing.assert_array_equal(b[:256], a)
     np.testing.assert_array_equal(b[256:], a[::-1])
+    ids3 = np.concatenate([ids, ids[::-1], ids[perm]])                                          # three batches per launch
+    c3 = enc.encode_ids(ids3, np.full(768, 512, dtype=np.int32))                                # (wide-tile kernel)
+    np.testing.assert_array_equal(c3[:256], a)
+    np.testing.assert_array_equal(c3[256:512], a[::-1])
+    np.testing.assert_array_equal(c3[512:], a[perm])
     want = R.encode_padded(ref, ids[:6], lengths[:6])                                           # ~10 s of CPU
     m = _assert_parity(a[:6], want, cc_min=0.97)   # centring over 6 issues only: noisier than the batch-wide metric
     print("full-size slice", m)
