@@ -238,7 +238,7 @@ def test_oom_halving_and_threads(r4, monkeypatch):
     ths = [threading.Thread(target=work, args=(i,)) for i in range(4)]
     [t.start() for t in ths]
     [t.join() for t in ths]
-    np.testing.assert_array_equal(np.concatenate(outs), want)
+    np.testing.assert_array_equal(np.concatenate(outs), want[:40])
 
 
 # ------------------------------------------------------------------------------------------------ python surface
