@@ -217,13 +217,8 @@ lstm_wide_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant
 #pragma unroll
         for (int ch = 0; ch < kCh; ++ch) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) gxr[ch][i] = __ldg(gxp + ch * 4 + i);
+          for (int i = 0; i < 4; ++i) gxr[ch][i] = ldg_stream(gxp + ch * 4 + i);
           cr[ch] = (t == 0) ? make_float4(0.f, 0.f, 0.f, 0.f) : cp[ch];
-        }
-        if (t + 1 < T) {
-          const char* nx = reinterpret_cast<const char*>(gxp) + static_cast<long long>(b_pad) * out_pad * 16ll;
-#pragma unroll
-          for (int i = 0; i < 2; ++i) prefetch_l2(nx + i * 128);
         }
         if (threadIdx.x == 128 && ci == 0) IE_TRACE(7, t);
         mbar_wait(&tfull[ci], static_cast<uint32_t>(t & 1));
