@@ -216,8 +216,8 @@ lstm_wide_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant
         float4 cr[kCh];
 #pragma unroll
         for (int ch = 0; ch < kCh; ++ch) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) gxr[ch][i] = ldg_stream(gxp + ch * 4 + i);
+          ldg_stream8(reinterpret_cast<const float*>(gxp + ch * 4), gxr[ch][0], gxr[ch][1]);
+          ldg_stream8(reinterpret_cast<const float*>(gxp + ch * 4 + 2), gxr[ch][2], gxr[ch][3]);
           cr[ch] = (t == 0) ? make_float4(0.f, 0.f, 0.f, 0.f) : cp[ch];
         }
         if (threadIdx.x == 128 && ci == 0) IE_TRACE(7, t);

@@ -304,14 +304,12 @@ __device__ __forceinline__ void st_global_v8(void* p, uint32_t a, uint32_t b, ui
                : "memory");
 }
 
-// streaming 128-bit read-only load: no L1 allocation, evict-first in L2 (a once-read stream must not displace the
-// L2-resident weights)
-__device__ __forceinline__ float4 ldg_stream(const float4* p) {
-  float4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.f32 {%0, %1, %2, %3}, [%4];"
-               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+// streaming 256-bit read-only load (sm_100): no L1 allocation, evict-first in L2 -- a once-read stream must not
+// displace the L2-resident weights.  (The .L2::evict_first qualifier only exists for the 256-bit forms.)
+__device__ __forceinline__ void ldg_stream8(const float* p, float4& a, float4& b) {
+  asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
                : "l"(p));
-  return v;
 }
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
