@@ -217,6 +217,13 @@ class InferenceWrapper:
         lst = [cls.process_dict(d) for d in dataframe.to_dict(orient='records')]
         return pd.DataFrame(lst)
 
+    def _forward_pass(self, x):
+        """ids (B,T) right-padded -> last-layer hidden states as numpy (B,T,emb_sz), zero initial state
+        (inference.py:55-57: reset(); forward(x)[-1][-1].detach().cpu().numpy()).  Kept for interface parity; the bulk
+        path of this package never materialises this tensor on the host."""
+        ids = np.asarray(x.cpu() if hasattr(x, 'cpu') else x, dtype=np.int64)
+        return self.encoder.raw_features(ids)
+
     # ---- single issue ---------------------------------------------------------------------------
     def get_raw_features_from_ids(self, seq_ints):
         """ids (1,T) or (T,) -> torch.Tensor (1, T, emb_sz): hidden states of the last layer, zero initial state."""

@@ -151,3 +151,19 @@ def test_features_dictionary_and_writers(tmp_path):
     out = E.save_embeddings(str(tmp_path / "emb"), np.ones((2, 2400)))
     arr = np.load(out) if out.endswith(".npy") else None
     assert arr is None or (arr.dtype == np.dtype("<f4") and arr.shape == (2, 2400))
+
+
+def test_text_boundary_helpers_cpu_only():
+    """process_dict / RuleTokenizer are host-side boundary code (inference.py:92-123, :51-53): markers, fallback text."""
+    from code_intelligence_b200.inference import InferenceWrapper, RuleTokenizer, pass_through
+    d = InferenceWrapper.process_dict({"title": "Crash in  TFJob", "body": "It FAILS!!!!!"})
+    assert d["text"].startswith("xxxfldtitle ") and " xxxfldbody " in d["text"]
+    with pytest.raises(AssertionError):
+        InferenceWrapper.process_dict({"title": "x"})
+    assert InferenceWrapper.process_dict({"title": None, "body": "b"}) == {"text": "xxxUnk"}   # swallowed like the reference
+    assert pass_through(3) == 3
+    itos = ["xxunk", "xxpad", "xxbos", "xxfld", "xxmaj", "xxup", "xxrep", "xxwrep", "crash", "in", "it", "fails", "!"]
+    ids = RuleTokenizer(itos)("Crash in IT fails")
+    assert ids.dtype == np.int64 and ids[0] == 2 and list(ids[1:]) == [4, 8, 9, 5, 10, 11]   # xxmaj crash in xxup it fails
+    df = __import__("pandas").DataFrame({"title": ["a", "b"], "body": ["c", "d"]})
+    assert list(InferenceWrapper.process_df(df)["text"]) == ["xxxfldtitle a xxxfldbody c", "xxxfldtitle b xxxfldbody d"]
