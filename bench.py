@@ -229,7 +229,7 @@ def main():
         torch.cuda.synchronize(dev)
 
     # ---- launch plan: steps are submitted kPerLaunch at a time (3 x 256 rows per ie_encoder_encode call) ----------
-    kPerLaunch = 3
+    kPerLaunch = max(1, enc.max_batch // B)   # 3; 5 with the experimental IE_ROT=1 kernel (csrc/lstm_rot.cu)
     def plan(first, count, per_launch):
         # a remainder launch (count % per_launch steps) goes first, so that the LAST launch of a region -- whose
         # phase events feed the roofline -- is a full one
@@ -337,8 +337,9 @@ def main():
             "single_batch": {"value": single_value, "unit": "issues/s", "ms_per_step": ms_single / K,
                              "note": "same measurement with one batch of 256 per launch"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "tensor", "kernel": "lstm_wide_kernel (persistent recurrent kernel, 2400-wide layers, "
-                                   "%d batches in the last timed launch)" % batches,
+            "roofline": {"bound": "tensor", "kernel": "%s (persistent recurrent kernel, 2400-wide layers, "
+                                   "%d batches in the last timed launch)" % (
+                                       "lstm_rot_kernel" if batches > 3 else "lstm_wide_kernel", batches),
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "avg_launch_us": avg_launch_us,
                          "flop_per_launch": flop_per_launch,

@@ -36,6 +36,7 @@ PROTOTYPES = {
     "ie_encoder_raw_features": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
                                           C.c_void_p]),
     "ie_encoder_launch_count": (C.c_int64, [C.c_void_p]),
+    "ie_encoder_max_batch": (C.c_int32, [C.c_void_p]),
     "ie_encoder_last_phase_ms": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32]),
     "ie_debug_seq_trace": (C.c_int64, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64]),
     "ie_debug_umma_rate": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),

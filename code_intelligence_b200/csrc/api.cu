@@ -89,6 +89,10 @@ struct ie_encoder {
   std::vector<Layer> layers;   // plan A: u ~ out/148 units per CTA (N = 160 pair tiles at H = 2400): B <= 512
   std::vector<Layer> layersB;  // plan B: u = 32 (N = 256 pair tiles): three batches per launch (512 < B <= 768)
   int use_wide = 1, wide_checked = 0;
+  // experimental (IE_ROT=1): rotating item schedule (lstm_rot.cu), up to kRotMaxBatches batches per launch on plan B;
+  // IE_ROT=2 also routes 256..768 rows through it (for testing).  max_batch is what ie_encoder_encode accepts.
+  int use_rot = 0, rot_checked = 0;
+  int max_batch = IE_MAX_BATCH;
   DevBuf emb;  // bf16 [vocab, e_pad]
   bool emb_loaded = false;
   // workspace
@@ -126,6 +130,8 @@ struct ie_mlp {
 };
 
 namespace {
+
+constexpr int kStepStride = ie::kRotMaxBatches;  // step counters per (layer, timestep): one per batch of the launch
 
 int plan_layers(ie_encoder* h, std::vector<Layer>& layers, int u_fixed) {
   const ie_config& c = h->cfg;
@@ -198,8 +204,8 @@ int ensure_workspace(ie_encoder* h, int b_pad, int T, bool want_raw) {
       max_kh = std::max<long long>(max_kh, L.kh_pad);
     }
   const long long rows = static_cast<long long>(T) * b_pad;
-  CK(h->ids.reserve(static_cast<size_t>(IE_MAX_BATCH) * T * sizeof(int64_t)));
-  CK(h->lengths.reserve(IE_MAX_BATCH * sizeof(int)));
+  CK(h->ids.reserve(static_cast<size_t>(h->max_batch) * T * sizeof(int64_t)));
+  CK(h->lengths.reserve(h->max_batch * sizeof(int)));
   CK(h->err.reserve(sizeof(int), true));
   CK(h->x0.reserve(static_cast<size_t>(rows) * h->e_pad * sizeof(__nv_bfloat16)));
   // hidden-state rings: (T+1) slots of b_pad rows; slot 0 and the K padding columns must be zero
@@ -207,14 +213,14 @@ int ensure_workspace(ie_encoder* h, int b_pad, int T, bool want_raw) {
   const size_t ybytes = static_cast<size_t>(rows + b_pad) * max_kh * sizeof(__nv_bfloat16);
   for (int i = 0; i < 2; ++i) CK(h->y[i].reserve(ybytes, /*zero=*/true));
   CK(h->gx.reserve(static_cast<size_t>(rows) * 4 * max_out_pad * sizeof(float)));
-  CK(h->c.reserve(static_cast<size_t>(IE_MAX_BATCH) * max_out_pad * sizeof(float)));
-  const size_t pb = static_cast<size_t>(IE_MAX_BATCH) * max_out_pad * sizeof(float);
+  CK(h->c.reserve(static_cast<size_t>(h->max_batch) * max_out_pad * sizeof(float)));
+  const size_t pb = static_cast<size_t>(h->max_batch) * max_out_pad * sizeof(float);
   CK(h->pool_sum.reserve(pb));
   CK(h->pool_max.reserve(pb));
   CK(h->pool_last.reserve(pb));
-  CK(h->out.reserve(static_cast<size_t>(IE_MAX_BATCH) * 3 * c.emb_sz * sizeof(float)));
+  CK(h->out.reserve(static_cast<size_t>(h->max_batch) * 3 * c.emb_sz * sizeof(float)));
   if (want_raw) CK(h->raw.reserve(static_cast<size_t>(b_pad) * T * max_out_pad * sizeof(float)));
-  CK(h->step_done.reserve(static_cast<size_t>(c.n_layers) * T * 3 * sizeof(unsigned)));
+  CK(h->step_done.reserve(static_cast<size_t>(c.n_layers) * T * kStepStride * sizeof(unsigned)));
   return IE_OK;
 }
 
@@ -237,14 +243,27 @@ int run_encoder(ie_encoder* h, const int64_t* ids, const int32_t* lengths, int B
     if (!L.loaded) return fail(IE_ERR_STATE, "LSTM layer weights not loaded");
   for (const Layer& L : h->layersB)
     if (!L.loaded) return fail(IE_ERR_STATE, "LSTM layer weights not loaded");
-  if (B < 1 || B > IE_MAX_BATCH) return fail(IE_ERR_INVALID, "B=%d outside [1,%d]", B, IE_MAX_BATCH);
+  if (B < 1 || B > h->max_batch) return fail(IE_ERR_INVALID, "B=%d outside [1,%d]", B, h->max_batch);
   if (T < 1) return fail(IE_ERR_INVALID, "T=%d must be >= 1", T);
   if (ids == nullptr || (out == nullptr && raw_out == nullptr)) return fail(IE_ERR_INVALID, "null pointer");
   const bool dev = (flags & IE_FLAG_DEVICE_PTRS) != 0;
   const bool pooled = out != nullptr;
-  const int b_pad = B <= 128 ? 128 : (B <= 256 ? 256 : (B <= 512 ? 512 : 768));
-  const bool wide = (b_pad == 768);
-  std::vector<Layer>& LS = wide ? h->layersB : h->layers;
+  const int b_pad = B <= 128 ? 128 : static_cast<int>(round_up(B, 256));
+  if (h->use_rot && !h->rot_checked) {  // every CTA pair of the rotating-schedule kernel must be co-resident
+    CK(cudaSetDevice(c.device));
+    for (const Layer& L : h->layersB) {
+      ie::LstmWideArgs q{};
+      q.T = 1; q.ng = 1; q.u = L.u; q.n_cta = L.n_cta; q.out_pad = L.out_pad; q.kh_pad = L.kh_pad;
+      q.num_sms = h->num_sms; q.check_only = 1;
+      if (ie::launch_lstm_rot(q, s) != cudaSuccess) h->use_rot = 0;
+    }
+    cudaGetLastError();
+    h->rot_checked = 1;
+  }
+  const bool rot = h->use_rot && b_pad >= 256 && (b_pad > 768 || h->use_rot >= 2);
+  const bool wide = (b_pad == 768) && !rot;
+  if (b_pad > 768 && !rot) return fail(IE_ERR_STATE, "B > 768 needs the rotating-schedule kernel (caller splits the batch)");
+  std::vector<Layer>& LS = (wide || rot) ? h->layersB : h->layers;
   // workspace cap (tokens per call); IE_MAX_TOKENS lowers it, e.g. to exercise the caller's batch-halving loop
   long long cap = 1ll << 21;
   if (const char* e = getenv("IE_MAX_TOKENS")) cap = std::max(128ll, atoll(e));
@@ -256,7 +275,7 @@ int run_encoder(ie_encoder* h, const int64_t* ids, const int32_t* lengths, int B
   if (rc != IE_OK) return rc;
 
   // lengths: validate on the host when we can; padded rows get length 1
-  std::vector<int> len_host(IE_MAX_BATCH, 1);
+  std::vector<int> len_host(h->max_batch, 1);
   if (pooled) {
     if (lengths == nullptr) return fail(IE_ERR_INVALID, "lengths is null");
     if (!dev) {
@@ -265,9 +284,9 @@ int run_encoder(ie_encoder* h, const int64_t* ids, const int32_t* lengths, int B
           return fail(IE_ERR_INVALID, "lengths[%d]=%d outside [1,%d]", b, lengths[b], T);
         len_host[b] = lengths[b];
       }
-      CK(cudaMemcpyAsync(h->lengths.p, len_host.data(), IE_MAX_BATCH * sizeof(int), cudaMemcpyHostToDevice, s));
+      CK(cudaMemcpyAsync(h->lengths.p, len_host.data(), h->max_batch * sizeof(int), cudaMemcpyHostToDevice, s));
     } else {
-      CK(cudaMemcpyAsync(h->lengths.p, len_host.data(), IE_MAX_BATCH * sizeof(int), cudaMemcpyHostToDevice, s));
+      CK(cudaMemcpyAsync(h->lengths.p, len_host.data(), h->max_batch * sizeof(int), cudaMemcpyHostToDevice, s));
       CK(cudaMemcpyAsync(h->lengths.p, lengths, B * sizeof(int), cudaMemcpyDeviceToDevice, s));
     }
   }
@@ -288,7 +307,7 @@ int run_encoder(ie_encoder* h, const int64_t* ids, const int32_t* lengths, int B
 
   const long long rows = static_cast<long long>(T) * b_pad;
   // persistent per-layer recurrent kernel: needs both 128-row halves and every CTA of a layer co-resident
-  bool seq = h->use_seq && b_pad >= 256 && !wide;
+  bool seq = h->use_seq && b_pad >= 256 && !wide && !rot;
   if (wide) {
     if (h->use_wide && !h->wide_checked) {
       for (const Layer& L : h->layersB) {
@@ -302,7 +321,7 @@ int run_encoder(ie_encoder* h, const int64_t* ids, const int32_t* lengths, int B
     }
     if (!h->use_wide) return fail(IE_ERR_STATE, "B > 512 needs the wide persistent kernel (caller splits the batch)");
   }
-  if ((seq || wide) && !h->seq_checked) {
+  if ((seq || wide) && !h->seq_checked) {  // (not needed by the rotating schedule, which runs every layer itself)
     for (const Layer& L : h->layers) {
       ie::LstmSeqArgs q{};
       q.T = 1; q.b_pad = 256; q.u = L.u; q.n_cta = L.n_cta; q.out_pad = L.out_pad; q.kh_pad = L.kh_pad;
@@ -312,8 +331,9 @@ int run_encoder(ie_encoder* h, const int64_t* ids, const int32_t* lengths, int B
     cudaGetLastError();
     h->seq_checked = 1;
   }
-  if (b_pad == 512 && !seq) return fail(IE_ERR_STATE, "B > 256 needs the persistent kernel (caller splits the batch)");
-  if (seq || wide) CK(cudaMemsetAsync(h->step_done.p, 0, static_cast<size_t>(c.n_layers) * T * 3 * sizeof(unsigned), s));
+  if (b_pad == 512 && !seq && !rot) return fail(IE_ERR_STATE, "B > 256 needs the persistent kernel (caller splits the batch)");
+  if (seq || wide || rot)
+    CK(cudaMemsetAsync(h->step_done.p, 0, static_cast<size_t>(c.n_layers) * T * kStepStride * sizeof(unsigned), s));
   // slot 0 of both hidden-state rings is h_{-1} = 0; a previous call with another B_pad may have written these rows
   for (int i = 0; i < 2; ++i)
     CK(cudaMemsetAsync(h->y[i].p, 0, static_cast<size_t>(b_pad) * h->y_ld * sizeof(__nv_bfloat16), s));
@@ -323,7 +343,7 @@ int run_encoder(ie_encoder* h, const int64_t* ids, const int32_t* lengths, int B
   // with three batches per launch the pooled last layer (narrow, latency bound) still runs the lstm_seq.cu kernel on its
   // plan-A layout when that is possible; all other layers use the wide tiles of plan B
   const Layer& lastA = h->layers.back();
-  const bool last_on_seq = wide && pooled && raw_out == nullptr && h->use_seq && lastA.u <= 12 && lastA.n_cta % 2 == 0 &&
+  const bool last_on_seq = wide && !rot && pooled && raw_out == nullptr && h->use_seq && lastA.u <= 12 && lastA.n_cta % 2 == 0 &&
                            (c.n_layers < 2 || lastA.kin_pad == h->layersB[c.n_layers - 1].kin_pad);
   for (int l = 0; l < c.n_layers; ++l) {
     const bool last = (l == c.n_layers - 1);
@@ -375,11 +395,30 @@ int run_encoder(ie_encoder* h, const int64_t* ids, const int32_t* lengths, int B
     a.kh_pad = L.kh_pad;
     a.ldy = h->y_ld;
     a.raw_ld = L.out_pad;
-    if (wide && !(last && last_on_seq)) {
+    if (rot) {
       ie::LstmWideArgs q{};
       q.tm_h = a.tm_h; q.tm_w = a.tm_w; q.gx = a.gx; q.c = a.c; q.y = a.y; q.raw = a.raw;
       q.pool_sum = a.pool_sum; q.pool_max = a.pool_max; q.pool_last = a.pool_last; q.lengths = a.lengths;
-      q.step_done = h->step_done.as<unsigned>() + static_cast<size_t>(l) * T * 3;
+      q.step_done = h->step_done.as<unsigned>() + static_cast<size_t>(l) * T * kStepStride;
+      q.T = T; q.ng = b_pad / 256; q.u = L.u; q.n_cta = L.n_cta; q.out_pad = L.out_pad; q.kh_pad = L.kh_pad;
+      q.ldy = a.ldy; q.raw_ld = a.raw_ld; q.fast_math = h->fast_math; q.num_sms = h->num_sms; q.check_only = 0;
+      q.trace = nullptr;
+      if (l == h->trace_layer) {
+        const int pairs = ie::lstm_rot_pairs(q);
+        const long long items = (static_cast<long long>(T) * q.ng * (L.n_cta / 2) + pairs - 1) / pairs;
+        CK(h->trace.reserve(static_cast<size_t>(2 * pairs) * items * 12 * sizeof(long long), true));
+        q.trace = h->trace.as<long long>();
+        q.trace_items = static_cast<int>(items);
+        h->trace_T = static_cast<int>(items);
+        h->trace_ctas = 2 * pairs;
+      }
+      CK(ie::launch_lstm_rot(q, s));
+      h->launches += 1;
+    } else if (wide && !(last && last_on_seq)) {
+      ie::LstmWideArgs q{};
+      q.tm_h = a.tm_h; q.tm_w = a.tm_w; q.gx = a.gx; q.c = a.c; q.y = a.y; q.raw = a.raw;
+      q.pool_sum = a.pool_sum; q.pool_max = a.pool_max; q.pool_last = a.pool_last; q.lengths = a.lengths;
+      q.step_done = h->step_done.as<unsigned>() + static_cast<size_t>(l) * T * kStepStride;
       q.T = T; q.ng = 3; q.u = L.u; q.n_cta = L.n_cta; q.out_pad = L.out_pad; q.kh_pad = L.kh_pad;
       q.ldy = a.ldy; q.raw_ld = a.raw_ld; q.fast_math = h->fast_math; q.num_sms = h->num_sms; q.check_only = 0;
       q.trace = nullptr;
@@ -396,7 +435,7 @@ int run_encoder(ie_encoder* h, const int64_t* ids, const int32_t* lengths, int B
       ie::LstmSeqArgs q{};
       q.tm_h = a.tm_h; q.tm_w = a.tm_w; q.gx = a.gx; q.y = a.y; q.raw = a.raw;
       q.pool_sum = a.pool_sum; q.pool_max = a.pool_max; q.pool_last = a.pool_last; q.lengths = a.lengths;
-      q.step_done = h->step_done.as<unsigned>() + static_cast<size_t>(l) * T * 3;
+      q.step_done = h->step_done.as<unsigned>() + static_cast<size_t>(l) * T * kStepStride;
       q.T = T; q.b_pad = b_pad; q.u = L.u; q.n_cta = L.n_cta; q.out_pad = L.out_pad; q.kh_pad = L.kh_pad;
       q.ldy = a.ldy; q.raw_ld = a.raw_ld; q.check_only = 0;
       q.fast_math = h->fast_math;
@@ -422,7 +461,7 @@ int run_encoder(ie_encoder* h, const int64_t* ids, const int32_t* lengths, int B
     cur ^= 1;
   }
 
-  const Layer& LL = last_on_seq ? h->layers.back() : LS.back();
+  const Layer& LL = (last_on_seq && !rot) ? h->layers.back() : LS.back();
   if (pooled) {
     float* out_dev = dev ? out : h->out.as<float>();
     CK(ie::launch_pool_finalize(h->pool_sum.as<float>(), h->pool_max.as<float>(), h->pool_last.as<float>(),
@@ -478,6 +517,8 @@ int ie_encoder_create(const ie_config* cfg, ie_encoder** out) {
   h->cfg = *cfg;
   h->num_sms = sms;
   if (const char* e = getenv("IE_SEQ")) h->use_seq = atoi(e);
+  if (const char* e = getenv("IE_ROT")) h->use_rot = atoi(e);
+  if (h->use_rot) h->max_batch = 256 * ie::kRotMaxBatches;
   h->fast_math = (cfg->flags & IE_CFG_ACCURATE_GATES) ? 0 : 1;
   if (const char* e = getenv("IE_FAST_MATH")) h->fast_math = atoi(e);
   int rc = plan_layers(h, h->layers, 0);
@@ -542,6 +583,16 @@ int ie_encoder_load_layer(ie_encoder* h, int32_t layer, const float* w_ih, const
 static int encode_locked(ie_encoder* h, const int64_t* ids, const int32_t* lengths, int B, int T, float* out, int flags,
                          cudaStream_t s) {
   const long long ow = 3ll * h->cfg.emb_sz;
+  if (B > IE_MAX_BATCH) {  // only reachable with the experimental rotating schedule (max_batch > IE_MAX_BATCH)
+    if (h->use_rot) {
+      const int rc = run_encoder(h, ids, lengths, B, T, out, nullptr, flags, s);
+      if (rc != IE_ERR_STATE || h->use_rot) return rc;
+    }
+    const int rc = encode_locked(h, ids, lengths, IE_MAX_BATCH, T, out, flags, s);
+    if (rc != IE_OK) return rc;
+    return encode_locked(h, ids + static_cast<long long>(IE_MAX_BATCH) * T, lengths + IE_MAX_BATCH, B - IE_MAX_BATCH, T,
+                         out + IE_MAX_BATCH * ow, flags, s);
+  }
   if (B > 512) {
     if (h->use_wide) {
       const int rc = run_encoder(h, ids, lengths, B, T, out, nullptr, flags, s);
@@ -568,7 +619,7 @@ int ie_encoder_encode(ie_encoder* h, const int64_t* ids, const int32_t* lengths,
   if (h == nullptr) return fail(IE_ERR_INVALID, "null handle");
   if (out == nullptr) return fail(IE_ERR_INVALID, "out is null");
   if (ids == nullptr || lengths == nullptr) return fail(IE_ERR_INVALID, "null pointer");
-  if (B < 1 || B > IE_MAX_BATCH) return fail(IE_ERR_INVALID, "B=%d outside [1,%d]", B, IE_MAX_BATCH);
+  if (B < 1 || B > h->max_batch) return fail(IE_ERR_INVALID, "B=%d outside [1,%d]", B, h->max_batch);
   std::lock_guard<std::mutex> lk(h->mu);
   // device-pointer mode: `stream` is used verbatim (NULL = the legacy default stream, e.g. torch's default);
   // host-pointer mode: NULL selects the handle's own stream
@@ -586,6 +637,8 @@ int ie_encoder_raw_features(ie_encoder* h, const int64_t* ids, int32_t B, int32_
 }
 
 int64_t ie_encoder_launch_count(const ie_encoder* h) { return h ? h->launches : 0; }
+
+int32_t ie_encoder_max_batch(const ie_encoder* h) { return h ? h->max_batch : IE_MAX_BATCH; }
 
 // debug: request a per-step timeline of `layer` in the persistent kernel on the next encode (layer < 0: off);
 // with out != NULL copy the last recorded timeline [n_cta][T][8] (SM clocks) and return n_cta*T

@@ -93,8 +93,15 @@ struct LstmWideArgs {
   long long ldy, raw_ld;
   int fast_math, num_sms, check_only;
   long long* trace;  // optional [grid][T][12] timeline (debug)
+  int trace_items;   // lstm_rot.cu only: the timeline is [grid][trace_items][12], one record per work item of the pair
 };
 cudaError_t launch_lstm_wide(const LstmWideArgs& a, cudaStream_t stream);
+
+// ---- persistent recurrent layer, rotating item schedule (lstm_rot.cu; experimental, IE_ROT=1): same arguments, up to
+//      kRotMaxBatches batches of 256 rows per launch; (timestep, batch, tile) items dealt round-robin over all CTA pairs
+constexpr int kRotMaxBatches = 5;
+cudaError_t launch_lstm_rot(const LstmWideArgs& a, cudaStream_t stream);
+int lstm_rot_pairs(const LstmWideArgs& a);  // CTA pairs the launch will use
 
 // ---- UMMA issue/throughput micro-benchmark (umma_bench.cu, debug) ------------------------------------------------
 cudaError_t run_umma_rate(int mode, int n, int iters, int commit_every, int grid, int ntiles, long long* host_out);

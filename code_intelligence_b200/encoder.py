@@ -95,7 +95,7 @@ class IssueEncoder:
     # ------------------------------------------------------------------ hot path
     def encode_ids(self, ids, lengths=None) -> np.ndarray:
         """ids (B,T) int64 right-padded with pad_idx, lengths (B,) -> (B, 3*emb_sz) float32 numpy.
-        B may exceed IE_MAX_BATCH; it is then processed in slices of IE_MAX_BATCH rows."""
+        B may exceed `max_batch` (IE_MAX_BATCH by default); it is then processed in slices of that many rows."""
         ids = np.ascontiguousarray(np.asarray(ids.cpu() if hasattr(ids, "cpu") else ids), dtype=np.int64)
         if ids.ndim != 2:
             raise ValueError("ids must be (B, T)")
@@ -105,8 +105,9 @@ class IssueEncoder:
         lengths = np.ascontiguousarray(np.asarray(lengths), dtype=np.int32)
         assert lengths.shape[0] == B, 'Number of elements in lengths should match the first dimension of ids'
         out = np.empty((B, self.out_dim), dtype=np.float32)
-        for b0 in range(0, B, IE_MAX_BATCH):
-            b1 = min(B, b0 + IE_MAX_BATCH)
+        mb = self.max_batch
+        for b0 in range(0, B, mb):
+            b1 = min(B, b0 + mb)
             sl = np.ascontiguousarray(ids[b0:b1])
             ln = np.ascontiguousarray(lengths[b0:b1])
             o = out[b0:b1]
@@ -134,11 +135,16 @@ class IssueEncoder:
         if ids.ndim != 2:
             raise ValueError("ids must be (B, T)")
         B, T = ids.shape
-        if B > IE_MAX_BATCH:
-            raise ValueError(f"B={B} > {IE_MAX_BATCH}")
+        if B > self.max_batch:
+            raise ValueError(f"B={B} > {self.max_batch}")
         raw = np.empty((B, T, self.emb_sz), dtype=np.float32)
         check(self._lib.ie_encoder_raw_features(self._h, ids.ctypes.data, B, T, raw.ctypes.data, 0, None))
         return raw
+
+    @property
+    def max_batch(self) -> int:
+        """Rows one C-ABI encode call takes: IE_MAX_BATCH (768), or 1280 with the experimental IE_ROT=1 kernel."""
+        return int(self._lib.ie_encoder_max_batch(self._h))
 
     @property
     def launch_count(self) -> int:
@@ -162,5 +168,5 @@ class IssueEncoder:
         with pad_idx, encode, unsort with argsort(argsort); on RuntimeError (CUDA OOM) halve bs and retry.
         Returns (N, 3*emb_sz) float32 in input order."""
         from .bulk import encode_sorted_batches
-        return encode_sorted_batches(docs, self.encode_ids, self.pad_idx, self.out_dim, bs=bs, max_bs=IE_MAX_BATCH,
+        return encode_sorted_batches(docs, self.encode_ids, self.pad_idx, self.out_dim, bs=bs, max_bs=self.max_batch,
                                      min_batches_rule=min_batches_rule)

@@ -191,6 +191,30 @@ def test_edge_cases_and_errors(r4):
     assert np.isfinite(enc.encode_ids(ids[:2], lengths[:2])).all()            # handle still usable
 
 
+def test_rotating_schedule_kernel_matches_default(monkeypatch):
+    """Opt-in IE_ROT kernel (csrc/lstm_rot.cu: up to five batches per launch, work items rotating over the CTA pairs):
+    same MMA tile shapes and K order per (row, unit) as the default kernels => identical bits, pooled and raw."""
+    from code_intelligence_b200 import IssueEncoder
+    n_layers, emb_sz, n_hid, vocab = 3, 96, 200, 500
+    emb, layers = R.make_encoder(7, vocab, emb_sz, n_hid, n_layers).export_weights()
+    monkeypatch.delenv("IE_ROT", raising=False)
+    base = IssueEncoder(n_layers, emb_sz, n_hid, vocab).load_weights(emb, layers)
+    monkeypatch.setenv("IE_ROT", "2")              # read at handle creation; 2 = also route 257..768 rows through it
+    rot = IssueEncoder(n_layers, emb_sz, n_hid, vocab).load_weights(emb, layers)
+    monkeypatch.delenv("IE_ROT")
+    assert base.max_batch == 768 and rot.max_batch == 1280
+    for B, T in ((300, 19), (700, 23), (1100, 17), (1280, 9)):
+        docs = R.synthetic_ids(B, T, seed=B + T, vocab_sz=vocab, min_len=1)
+        ids, lengths = _pad(docs, T)
+        want = base.encode_ids(ids, lengths)
+        got = rot.encode_ids(ids, lengths)
+        np.testing.assert_array_equal(got, want)
+        if B <= 768:
+            np.testing.assert_array_equal(rot.raw_features(ids), base.raw_features(ids))
+    base.close()
+    rot.close()
+
+
 def test_full_size_batch_properties(r4):
     """BASELINE.json configs[1] shape (batch 256, seq_len 512): size-independent properties + oracle on a slice."""
     enc, ref = r4

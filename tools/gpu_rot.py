@@ -1,0 +1,120 @@
+"""Development aid (not product, not a test): check the experimental rotating-schedule recurrent kernel (IE_ROT,
+csrc/lstm_rot.cu) against the default kernels of the same library -- the two must agree bit for bit, because every
+(row, unit) sees the same MMA tile shapes in the same K order -- and time both on the R4 encoder.
+
+    python tools/gpu_rot.py [--T 512] [--iters 3] [--skip-small] [--log gpurun_out/rot.jsonl]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def rand_weights(n_layers, emb_sz, n_hid, vocab, seed=1234):
+    rng = np.random.default_rng(seed)
+    emb = rng.uniform(-0.1, 0.1, (vocab, emb_sz)).astype(np.float32)
+    layers = []
+    for l in range(n_layers):
+        n_in = emb_sz if l == 0 else n_hid
+        n_out = emb_sz if l == n_layers - 1 else n_hid
+        k = 1.0 / np.sqrt(n_out)
+        layers.append(dict(w_ih=rng.uniform(-k, k, (4 * n_out, n_in)).astype(np.float32),
+                           w_hh=rng.uniform(-k, k, (4 * n_out, n_out)).astype(np.float32),
+                           b_ih=rng.uniform(-k, k, 4 * n_out).astype(np.float32),
+                           b_hh=rng.uniform(-k, k, 4 * n_out).astype(np.float32)))
+    return emb, layers
+
+
+def make(cfg, weights, rot):
+    from code_intelligence_b200 import IssueEncoder
+    if rot:
+        os.environ["IE_ROT"] = str(rot)
+    else:
+        os.environ.pop("IE_ROT", None)
+    enc = IssueEncoder(*cfg, 1, 0).load_weights(*weights)
+    os.environ.pop("IE_ROT", None)
+    return enc
+
+
+def ids_lengths(B, T, vocab, seed, ragged=True):
+    rng = np.random.default_rng(seed)
+    lengths = rng.integers(max(1, T // 3), T + 1, B).astype(np.int32) if ragged else np.full(B, T, np.int32)
+    lengths[0] = T
+    ids = rng.integers(2, vocab, (B, T)).astype(np.int64)
+    for b in range(B):
+        ids[b, lengths[b]:] = 1
+    return ids, lengths
+
+
+def compare(name, cfg, weights, cases, log):
+    base = make(cfg, weights, 0)
+    rot = make(cfg, weights, 2)
+    assert rot.max_batch == 1280 and base.max_batch == 768, (rot.max_batch, base.max_batch)
+    for (B, T) in cases:
+        ids, lengths = ids_lengths(B, T, cfg[3], seed=B * 131 + T)
+        t0 = time.time()
+        want = base.encode_ids(ids, lengths)
+        got = rot.encode_ids(ids, lengths)
+        rec = dict(check=name, B=B, T=T, equal=bool(np.array_equal(got, want)), finite=bool(np.isfinite(got).all()),
+                   max_abs=float(np.abs(got - want).max()), nbad_rows=int((np.abs(got - want).max(axis=1) > 0).sum()),
+                   sec=round(time.time() - t0, 2))
+        if B <= 768 and T <= 64:
+            raw_w, raw_g = base.raw_features(ids), rot.raw_features(ids)
+            rec["raw_equal"] = bool(np.array_equal(raw_w, raw_g))
+        print(json.dumps(rec), flush=True)
+        log.write(json.dumps(rec) + "\n")
+        log.flush()
+    return base, rot
+
+
+def timeit(enc, B, T, vocab, iters):
+    import torch
+    ids, lengths = ids_lengths(B, T, vocab, seed=7, ragged=False)
+    ids_d = torch.from_numpy(ids).cuda()
+    len_d = torch.from_numpy(lengths).cuda()
+    out = torch.empty((B, enc.out_dim), dtype=torch.float32, device="cuda")
+    for _ in range(2):
+        enc.encode_ids_device(ids_d, len_d, out)
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ev[0].record()
+    for _ in range(iters):
+        enc.encode_ids_device(ids_d, len_d, out)
+    ev[1].record()
+    torch.cuda.synchronize()
+    ms = ev[0].elapsed_time(ev[1]) / iters
+    ph = enc.last_phase_ms()
+    return dict(B=B, T=T, ms=round(ms, 3), issues_per_s=round(B / ms * 1e3, 1), ms_per_256=round(ms * 256 / B, 3),
+                gemm=[round(x, 2) for x in ph["gemm"]], steps=[round(x, 2) for x in ph["steps"]])
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--T", type=int, default=512)
+    ap.add_argument("--iters", type=int, default=3)
+    ap.add_argument("--skip-small", action="store_true")
+    ap.add_argument("--log", default=os.path.join(ROOT, "gpurun_out", "rot.jsonl"))
+    a = ap.parse_args()
+    os.makedirs(os.path.dirname(a.log), exist_ok=True)
+    log = open(a.log, "a")
+    if not a.skip_small:
+        cfg = (3, 96, 200, 500)
+        compare("small", cfg, rand_weights(*cfg), [(300, 19), (700, 23), (1100, 17), (1280, 9)], log)
+    cfg = (4, 800, 2400, 60000)
+    base, rot = compare("r4", cfg, rand_weights(*cfg), [(768, 24), (1280, 40)], log)
+    for enc, B, tag in ((base, 768, "wide"), (rot, 1280, "rot5"), (rot, 768, "rot3")):
+        rec = timeit(enc, B, a.T, cfg[3], a.iters)
+        rec["path"] = tag
+        print(json.dumps(rec), flush=True)
+        log.write(json.dumps(rec) + "\n")
+        log.flush()
+
+
+if __name__ == "__main__":
+    main()
