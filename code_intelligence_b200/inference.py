@@ -97,23 +97,28 @@ def _deal_caps(toks):
     return res
 
 
-_TOKEN_RE = re.compile(r"xxx?[a-z_]+|\w+(?:'\w+)?|[^\w\s]", re.UNICODE)
+TEXT_SPEC_TOK = [UNK, PAD, BOS, FLD, TK_MAJ, TK_UP, TK_REP, TK_WREP]   # fastai defaults.text_spec_tok
 
 
 class RuleTokenizer:
-    """Approximate stand-in for fastai's ``Tokenizer(SpacyTokenizer('en'))``: fastai pre/post rules restated,
-    regex word splitting instead of spaCy.  NOT parity-pinned against spaCy (next row)."""
+    """Stand-in for fastai 1.0.53's ``Tokenizer(SpacyTokenizer('en'))`` when fastai/spaCy are not installed:
+    ``Tokenizer.process_text`` restated -- default pre-rules, the word splitter (``tokenizer.SpacyLikeTokenizer``, a
+    restatement of spaCy's rule tokenizer with fastai's special tokens registered as special cases), default
+    post-rules -- then the vocab lookup of ``Vocab.numericalize`` (unknown -> xxunk).  NOT parity-pinned against
+    spaCy (row f-1 of SURVEY.md section 8; no spaCy in this image)."""
 
     def __init__(self, itos: List[str]):
+        from .tokenizer import SpacyLikeTokenizer
         self.itos = list(itos)
         self.stoi = {s: i for i, s in reversed(list(enumerate(self.itos)))}
         self.unk = self.stoi.get(UNK, 0)
         self.bos = self.stoi.get(BOS, 2)
+        self.splitter = SpacyLikeTokenizer(TEXT_SPEC_TOK)
 
     def tokens(self, text: str) -> List[str]:
         for r in TEXT_PRE_RULES:
             text = r(text)
-        toks = _TOKEN_RE.findall(text)
+        toks = self.splitter(text)
         return _deal_caps(_replace_all_caps(toks))
 
     def __call__(self, text: str) -> np.ndarray:

@@ -167,3 +167,49 @@ def test_text_boundary_helpers_cpu_only():
     assert ids.dtype == np.int64 and ids[0] == 2 and list(ids[1:]) == [4, 8, 9, 5, 10, 11]   # xxmaj crash in xxup it fails
     df = __import__("pandas").DataFrame({"title": ["a", "b"], "body": ["c", "d"]})
     assert list(InferenceWrapper.process_df(df)["text"]) == ["xxxfldtitle a xxxfldbody c", "xxxfldtitle b xxxfldbody d"]
+
+
+def test_spacy_like_tokenizer_documented_cases():
+    """Row f-1: the word splitter used when fastai/spaCy are absent.  Expected outputs are the
+    behaviours spaCy documents for its English tokenizer (usage docs' "Let's go to N.Y.!" walk-through, the
+    contraction / punctuation / unit / hyphen cases of spacy/tests/lang/en) -- unpinned against a live spaCy."""
+    from code_intelligence_b200.tokenizer import SpacyLikeTokenizer
+    tok = SpacyLikeTokenizer(["xxbos", "xxfld", "xxmaj", "xxup", "xxrep", "xxwrep", "xxunk", "xxpad"])
+    cases = {
+        "Let's go to N.Y.!": ["Let", "'s", "go", "to", "N.Y.", "!"],
+        "I don't think we can't.": ["I", "do", "n't", "think", "we", "ca", "n't", "."],
+        "I'm here, it's fine; they're late": ["I", "'m", "here", ",", "it", "'s", "fine", ";", "they", "'re", "late"],
+        "Hello, world.": ["Hello", ",", "world", "."],
+        "(foo) [bar]": ["(", "foo", ")", "[", "bar", "]"],
+        "It costs $10.50, i.e. 10% of 10km...": ["It", "costs", "$", "10.50", ",", "i.e.", "10", "%", "of", "10", "km",
+                                                 "..."],
+        "a well-known fix": ["a", "well", "-", "known", "fix"],
+        "The U.K. and e.g. Mr. Smith": ["The", "U.K.", "and", "e.g.", "Mr.", "Smith"],
+        "ok :) <3": ["ok", ":)", "<3"],
+        "a\n\nb \n c": ["a", "\n\n", "b", "\n ", "c"],          # whitespace runs other than one space are tokens
+        "x=y a:b 1-2 end.Start": ["x", "=", "y", "a", ":", "b", "1", "-", "2", "end", ".", "Start"],
+        "see http://example.com/a?b=c now": ["see", "http://example.com/a?b=c", "now"],
+        "cannot gonna": ["can", "not", "gon", "na"],
+        "xxbos xxmaj hello xxrep 4 !": ["xxbos", "xxmaj", "hello", "xxrep", "4", "!"],
+        "C++ and .NET v1.2.3": ["C++", "and", ".NET", "v1.2.3"],
+        "": [],
+    }
+    for text, want in cases.items():
+        assert tok(text) == want, (text, tok(text))
+    # every character except single separating spaces survives tokenisation, in order
+    for text in cases:
+        assert "".join(tok(text)).replace(" ", "") == text.replace(" ", "")
+
+
+def test_rule_tokenizer_process_text_pipeline():
+    """fastai Tokenizer.process_text restated: pre-rules -> splitter -> post-rules -> vocab lookup."""
+    from code_intelligence_b200.inference import RuleTokenizer
+    itos = ['xxunk', 'xxpad', 'xxbos', 'xxfld', 'xxmaj', 'xxup', 'xxrep', 'xxwrep', 'wow', '!', 'this', 'is', 'cool',
+            '5', "n't", 'does', 'work', '#', '12', '/']
+    rt = RuleTokenizer(itos)
+    toks = rt.tokens("WOW!!!!! This is is is is is cool")
+    assert toks == ['xxup', 'wow', 'xxrep', '5', '!', 'xxmaj', 'this', 'xxwrep', '5', 'is', 'cool'], toks
+    ids = rt("Doesn't work #12 a/b")
+    want = ['xxbos', 'xxmaj', 'does', "n't", 'work', '#', '12', 'xxunk', '/', 'xxunk']
+    assert [itos[i] for i in ids] == want, [itos[i] for i in ids]
+    assert ids.dtype == np.int64 and ids[0] == 2
