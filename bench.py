@@ -78,21 +78,39 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.p.terminate()
         time.sleep(0.05)
-        sm, mx, reasons = [], [], set()
+        return self.summarise(self.rows)
+
+    @staticmethod
+    def summarise(rows):
+        """Median SM clock and board power over the samples taken UNDER LOAD (power >= 60 % of the highest sample: the
+        sampler also sees the idle gaps between the arms, where the clock sits at its maximum)."""
+        samples, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in rows:
             try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
+                clk, cmax = float(r[1]), float(r[2])
             except Exception:
                 continue
+            try:
+                pw = float(r[3])
+            except Exception:
+                pw = None
+            samples.append((clk, pw))
+            mx.append(cmax)
             for nm, v in zip(names, r[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
-        sm.sort()
-        # under load = the upper half of the samples (the sampler also sees idle gaps)
-        med = sm[len(sm) * 3 // 4] if sm else None
-        return {"sm_mhz": med, "sm_max_mhz": (max(mx) if mx else None), "reasons": sorted(reasons),
-                "samples": len(sm)}
+        powers = [pw for _, pw in samples if pw is not None]
+        if powers:
+            thr = 0.6 * max(powers)
+            loaded = [(c, pw) for c, pw in samples if pw is not None and pw >= thr]
+        else:
+            loaded = samples
+        clks = sorted(c for c, _ in loaded)
+        pws = sorted(pw for _, pw in loaded if pw is not None)
+        return {"sm_mhz": (clks[len(clks) // 2] if clks else None), "sm_max_mhz": (max(mx) if mx else None),
+                "reasons": sorted(reasons), "samples": len(samples), "samples_under_load": len(loaded),
+                "power_w": (pws[len(pws) // 2] if pws else None), "power_w_max": (max(powers) if powers else None)}
 
 
 def usable_cpus():

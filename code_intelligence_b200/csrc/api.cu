@@ -40,10 +40,19 @@ int cuda_fail(cudaError_t e, const char* what) {
 
 inline long long round_up(long long x, long long m) { return (x + m - 1) / m * m; }
 
-// grow-only device buffer
+// grow-only device buffer; owns its allocation (freed on destruction, so error paths do not leak)
 struct DevBuf {
   void* p = nullptr;
   size_t cap = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf(DevBuf&& o) noexcept : p(o.p), cap(o.cap) { o.p = nullptr; o.cap = 0; }
+  DevBuf& operator=(DevBuf&& o) noexcept {
+    if (this != &o) { release(); p = o.p; cap = o.cap; o.p = nullptr; o.cap = 0; }
+    return *this;
+  }
+  ~DevBuf() { release(); }
   cudaError_t reserve(size_t bytes, bool zero = false) {
     if (bytes <= cap) return cudaSuccess;
     if (p) cudaFree(p);

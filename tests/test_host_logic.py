@@ -213,3 +213,14 @@ def test_rule_tokenizer_process_text_pipeline():
     want = ['xxbos', 'xxmaj', 'does', "n't", 'work', '#', '12', 'xxunk', '/', 'xxunk']
     assert [itos[i] for i in ids] == want, [itos[i] for i in ids]
     assert ids.dtype == np.int64 and ids[0] == 2
+
+
+def test_bench_clock_sampler_summary():
+    """bench.py's `clocks` key: the median SM clock / power over the samples taken under load, throttle reasons."""
+    import bench
+    idle = ["0", "1965", "1965", "180.2", "x", "Not Active", "Not Active", "Not Active", "Not Active"]
+    busy = ["0", "1400", "1965", "990.1", "x", "Not Active", "Not Active", "Not Active", "Active"]
+    s = bench.ClockSampler.summarise([idle] * 5 + [busy] * 7 + [["garbage"]])
+    assert s["sm_mhz"] == 1400.0 and s["sm_max_mhz"] == 1965.0 and s["reasons"] == ["sw_power_cap"]
+    assert s["samples"] == 12 and s["samples_under_load"] == 7 and s["power_w"] == 990.1
+    assert bench.ClockSampler.summarise([])["sm_mhz"] is None
