@@ -102,6 +102,13 @@ struct ie_encoder {
   // IE_ROT=2 also routes 256..768 rows through it (for testing).  max_batch is what ie_encoder_encode accepts.
   int use_rot = 0, rot_checked = 0;
   int max_batch = IE_MAX_BATCH;
+  // experimental (IE_EMB_PROJ=1): layer 0's input projection W_ih0 . Emb[id] + b is a function of the token id alone,
+  // so it is tabulated once per weight set (proj: [vocab_pad, 4*out_pad] f32, plan-B column order, computed by the same
+  // GEMM from the same bf16 operands => the same bits) and the wide / rotating kernels read row tok[t, b] of it:
+  // no embedding gather, no layer-0 GEMM, no Gx write for that layer.
+  int use_proj = 0;
+  bool proj_built = false;
+  DevBuf proj, tok;
   DevBuf emb;  // bf16 [vocab, e_pad]
   bool emb_loaded = false;
   // workspace
@@ -230,6 +237,7 @@ int ensure_workspace(ie_encoder* h, int b_pad, int T, bool want_raw) {
   CK(h->out.reserve(static_cast<size_t>(h->max_batch) * 3 * c.emb_sz * sizeof(float)));
   if (want_raw) CK(h->raw.reserve(static_cast<size_t>(b_pad) * T * max_out_pad * sizeof(float)));
   CK(h->step_done.reserve(static_cast<size_t>(c.n_layers) * T * kStepStride * sizeof(unsigned)));
+  if (h->use_proj) CK(h->tok.reserve(static_cast<size_t>(rows) * sizeof(int)));
   return IE_OK;
 }
 
@@ -240,6 +248,36 @@ int mark(ie_encoder* h, cudaStream_t s) {
     h->ev.push_back(e);
   }
   CK(cudaEventRecord(h->ev[h->ev_used++], s));
+  return IE_OK;
+}
+
+// IE_EMB_PROJ: tabulate layer 0's input projection for every token id (once per weight set)
+int build_proj_table(ie_encoder* h, cudaStream_t s) {
+  const Layer& L = h->layersB[0];
+  const long long v_pad = round_up(h->cfg.vocab_sz, 256);
+  if (h->emb.cap < static_cast<size_t>(v_pad) * h->e_pad * sizeof(__nv_bfloat16))
+    return fail(IE_ERR_STATE, "embedding was loaded without row padding (IE_EMB_PROJ must be set before loading)");
+  CK(h->proj.reserve(static_cast<size_t>(v_pad) * 4 * L.out_pad * sizeof(float)));
+  ie::GemmArgs g{};
+  g.a = h->emb.as<__nv_bfloat16>();
+  g.lda = h->e_pad;
+  g.b = L.w_ih.as<__nv_bfloat16>();
+  g.ldb = L.kin_pad;
+  g.d = h->proj.p;
+  g.ldd = 4ll * L.out_pad;
+  g.bias = L.bias.as<float>();
+  g.m_pad = static_cast<int>(v_pad);
+  g.n_pad = 4 * L.out_pad;
+  g.k_pad = L.kin_pad;
+  g.m_store = static_cast<int>(v_pad);
+  g.n_store = 4 * L.out_pad;
+  g.bn = L.bn;
+  g.act = 0;
+  g.out_bf16 = 0;
+  g.num_sms = h->num_sms;
+  CK(ie::launch_gemm_bf16(g, s));
+  h->launches++;
+  h->proj_built = true;
   return IE_OK;
 }
 
@@ -308,9 +346,15 @@ int run_encoder(ie_encoder* h, const int64_t* ids, const int32_t* lengths, int B
   h->ev_used = 0;
   h->last_T = T;
   h->last_b_pad = b_pad;
+  // layer 0 from the per-token projection table (only the wide / rotating kernels take the token indirection)
+  const bool proj = h->use_proj && (wide || rot) && c.n_layers > 1;
+  if (proj && !h->proj_built && (rc = build_proj_table(h, s)) != IE_OK) return rc;
   if ((rc = mark(h, s)) != IE_OK) return rc;
-  CK(ie::launch_embed_gather(ids_dev, B, T, b_pad, h->emb.as<__nv_bfloat16>(), c.vocab_sz, h->e_pad,
-                             h->x0.as<__nv_bfloat16>(), h->e_pad, c.pad_idx, h->err.as<int>(), s));
+  if (proj)
+    CK(ie::launch_tokens_time_major(ids_dev, B, T, b_pad, c.vocab_sz, c.pad_idx, h->tok.as<int>(), h->err.as<int>(), s));
+  else
+    CK(ie::launch_embed_gather(ids_dev, B, T, b_pad, h->emb.as<__nv_bfloat16>(), c.vocab_sz, h->e_pad,
+                               h->x0.as<__nv_bfloat16>(), h->e_pad, c.pad_idx, h->err.as<int>(), s));
   h->launches++;
   if ((rc = mark(h, s)) != IE_OK) return rc;
 
@@ -375,8 +419,11 @@ int run_encoder(ie_encoder* h, const int64_t* ids, const int32_t* lengths, int B
     g.act = 0;
     g.out_bf16 = 0;
     g.num_sms = h->num_sms;
-    CK(ie::launch_gemm_bf16(g, s));
-    h->launches++;
+    const bool from_table = proj && l == 0;  // Gx rows of layer 0 are rows of the per-token table: no GEMM
+    if (!from_table) {
+      CK(ie::launch_gemm_bf16(g, s));
+      h->launches++;
+    }
     if ((rc = mark(h, s)) != IE_OK) return rc;
 
     // recurrence
@@ -388,7 +435,7 @@ int run_encoder(ie_encoder* h, const int64_t* ids, const int32_t* lengths, int B
     a.fast_math = h->fast_math;
     CK(ie::make_tmap_bf16_2d(&a.tm_hs, ybuf, L.kh_pad, static_cast<uint64_t>(rows + b_pad), h->y_ld, 64,
                              128 / L.cluster));
-    a.gx = h->gx.as<float>();
+    a.gx = from_table ? h->proj.as<float>() : h->gx.as<float>();
     a.c = h->c.as<float>();
     a.y = ybuf;
     a.raw = (last && raw_out != nullptr) ? h->raw.as<float>() : nullptr;
@@ -412,6 +459,7 @@ int run_encoder(ie_encoder* h, const int64_t* ids, const int32_t* lengths, int B
       q.T = T; q.ng = b_pad / 256; q.u = L.u; q.n_cta = L.n_cta; q.out_pad = L.out_pad; q.kh_pad = L.kh_pad;
       q.ldy = a.ldy; q.raw_ld = a.raw_ld; q.fast_math = h->fast_math; q.num_sms = h->num_sms; q.check_only = 0;
       q.trace = nullptr;
+      q.tok = from_table ? h->tok.as<int>() : nullptr;
       if (l == h->trace_layer) {
         const int pairs = ie::lstm_rot_pairs(q);
         const long long items = (static_cast<long long>(T) * q.ng * (L.n_cta / 2) + pairs - 1) / pairs;
@@ -431,6 +479,7 @@ int run_encoder(ie_encoder* h, const int64_t* ids, const int32_t* lengths, int B
       q.T = T; q.ng = 3; q.u = L.u; q.n_cta = L.n_cta; q.out_pad = L.out_pad; q.kh_pad = L.kh_pad;
       q.ldy = a.ldy; q.raw_ld = a.raw_ld; q.fast_math = h->fast_math; q.num_sms = h->num_sms; q.check_only = 0;
       q.trace = nullptr;
+      q.tok = from_table ? h->tok.as<int>() : nullptr;
       if (l == h->trace_layer) {
         const int grid = 2 * std::min(h->num_sms / 2, 3 * (L.n_cta / 2));
         CK(h->trace.reserve(static_cast<size_t>(grid) * T * 12 * sizeof(long long), true));
@@ -527,6 +576,7 @@ int ie_encoder_create(const ie_config* cfg, ie_encoder** out) {
   h->num_sms = sms;
   if (const char* e = getenv("IE_SEQ")) h->use_seq = atoi(e);
   if (const char* e = getenv("IE_ROT")) h->use_rot = atoi(e);
+  if (const char* e = getenv("IE_EMB_PROJ")) h->use_proj = atoi(e);
   if (h->use_rot) h->max_batch = 256 * ie::kRotMaxBatches;
   h->fast_math = (cfg->flags & IE_CFG_ACCURATE_GATES) ? 0 : 1;
   if (const char* e = getenv("IE_FAST_MATH")) h->fast_math = atoi(e);
@@ -546,7 +596,7 @@ void ie_encoder_destroy(ie_encoder* h) {
   for (Layer& L : h->layers) { L.w_ih.release(); L.w_hh.release(); L.bias.release(); }
   for (Layer& L : h->layersB) { L.w_ih.release(); L.w_hh.release(); L.bias.release(); }
   DevBuf* bufs[] = {&h->emb, &h->ids, &h->lengths, &h->x0, &h->y[0], &h->y[1], &h->gx, &h->c, &h->pool_sum,
-                    &h->pool_max, &h->pool_last, &h->out, &h->raw, &h->err, &h->step_done, &h->trace};
+                    &h->pool_max, &h->pool_last, &h->out, &h->raw, &h->err, &h->step_done, &h->trace, &h->proj, &h->tok};
   for (DevBuf* b : bufs) b->release();
   for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -557,11 +607,14 @@ int ie_encoder_load_embedding(ie_encoder* h, const float* emb) {
   if (h == nullptr || emb == nullptr) return fail(IE_ERR_INVALID, "null argument");
   std::lock_guard<std::mutex> lk(h->mu);
   CK(cudaSetDevice(h->cfg.device));
-  std::vector<int> ident(h->cfg.vocab_sz);
-  for (int i = 0; i < h->cfg.vocab_sz; ++i) ident[i] = i;
+  // IE_EMB_PROJ: the table GEMM reads the embedding as its A operand, so its rows are padded to whole M tiles (zeros)
+  const int v_rows = h->use_proj ? static_cast<int>(round_up(h->cfg.vocab_sz, 256)) : h->cfg.vocab_sz;
+  std::vector<int> ident(v_rows);
+  for (int i = 0; i < v_rows; ++i) ident[i] = i < h->cfg.vocab_sz ? i : -1;
   int rc = upload_sliced(emb, h->cfg.vocab_sz, h->cfg.emb_sz, ident, h->e_pad, h->emb, h->own_stream);
   if (rc != IE_OK) return rc;
   h->emb_loaded = true;
+  h->proj_built = false;
   return IE_OK;
 }
 
@@ -585,6 +638,7 @@ int ie_encoder_load_layer(ie_encoder* h, int32_t layer, const float* w_ih, const
     CK(cudaMemcpy(L.bias.p, bias.data(), bias.size() * sizeof(float), cudaMemcpyHostToDevice));
     L.loaded = true;
   }
+  if (layer == 0) h->proj_built = false;
   return IE_OK;
 }
 

@@ -94,6 +94,8 @@ struct LstmWideArgs {
   int fast_math, num_sms, check_only;
   long long* trace;  // optional [grid][T][12] timeline (debug)
   int trace_items;   // lstm_rot.cu only: the timeline is [grid][trace_items][12], one record per work item of the pair
+  const int* tok;    // optional [T*256*ng] time-major token ids: Gx row of (t, row) is gx[tok[t*b_pad+row]] (per-token
+                     // input-projection table of layer 0, api.cu IE_EMB_PROJ) instead of gx[t*b_pad+row]
 };
 cudaError_t launch_lstm_wide(const LstmWideArgs& a, cudaStream_t stream);
 
@@ -112,6 +114,9 @@ cudaError_t launch_embed_gather(const int64_t* ids, int B, int T, int b_pad, con
                                 int e_pad, __nv_bfloat16* x0, long long ldx, int pad_idx, int* err_flag,
                                 cudaStream_t stream);
 // out[b] = [sum/len | max | last], b < B, first `e` units
+// ids [B, T] int64 -> tok [T*b_pad] int32 time-major (rows >= B: pad_idx), range-checked like launch_embed_gather
+cudaError_t launch_tokens_time_major(const int64_t* ids, int B, int T, int b_pad, int vocab, int pad_idx, int* tok,
+                                     int* err_flag, cudaStream_t stream);
 cudaError_t launch_pool_finalize(const float* pool_sum, const float* pool_max, const float* pool_last,
                                  const int* lengths, int B, int e, int out_pad, float* out, cudaStream_t stream);
 // f32 [rows, cols] (row pitch ld_src) -> bf16 [rows_pad, ld_dst] with optional row permutation (src row of dst row r

@@ -30,13 +30,14 @@ constexpr int kWGW = 2, kWWStages = 3;  // W ring: 3 stages x 2 k-blocks x 16 KB
 constexpr int kTileN = 256;             // accumulator columns per tile = 64 hidden units
 constexpr int kHalfRows = 128;          // W rows each CTA of the pair contributes
 
+template <bool TOK>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kWThreads, 1)
 lstm_wide_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ CUtensorMap tm_w,
                  const float* __restrict__ gx, float* __restrict__ cstate, __nv_bfloat16* __restrict__ y,
                  float* __restrict__ raw, float* __restrict__ pool_sum, float* __restrict__ pool_max,
                  float* __restrict__ pool_last, const int* __restrict__ lengths, unsigned* __restrict__ step_done, int T,
                  int ng, int tiles, int out_pad, int num_k_blocks, long long ldy, long long raw_ld, int fast_math,
-                 long long* __restrict__ trace) {
+                 long long* __restrict__ trace, const int* __restrict__ tok) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t rawaddr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (rawaddr & 1023u)) & 1023u);
@@ -205,7 +206,9 @@ lstm_wide_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant
         const int brow = g * 256 + row;
         const int unit0 = j * 64 + cq * 16;
         const int len = pooled ? lengths[brow] : 1;
-        const float4* gxp = reinterpret_cast<const float4*>(gx + (static_cast<long long>(t) * b_pad + brow) * (4ll * out_pad) +
+        const long long grow = TOK ? static_cast<long long>(__ldg(tok + static_cast<long long>(t) * b_pad + brow))
+                                   : static_cast<long long>(t) * b_pad + brow;  // TOK: per-token projection table
+        const float4* gxp = reinterpret_cast<const float4*>(gx + grow * (4ll * out_pad) +
                                                             4ll * unit0);
         float4* cp = reinterpret_cast<float4*>(cstate + static_cast<long long>(brow) * out_pad + unit0);
         __nv_bfloat16* yrow = y + (static_cast<long long>(t + 1) * b_pad + brow) * ldy + unit0;
@@ -311,7 +314,9 @@ cudaError_t launch_lstm_wide(const LstmWideArgs& a, cudaStream_t stream) {
   const size_t smem = wide_smem_bytes();
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(lstm_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(lstm_wide_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(lstm_wide_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
@@ -322,13 +327,18 @@ cudaError_t launch_lstm_wide(const LstmWideArgs& a, cudaStream_t stream) {
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     int max_clusters = 0;
-    cudaError_t e = cudaOccupancyMaxActiveClusters(&max_clusters, lstm_wide_kernel, &cfg);
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&max_clusters, lstm_wide_kernel<false>, &cfg);
     if (e != cudaSuccess) return e;
     return max_clusters >= pairs ? cudaSuccess : cudaErrorCooperativeLaunchTooLarge;
   }
-  lstm_wide_kernel<<<2 * pairs, kWThreads, smem, stream>>>(a.tm_h, a.tm_w, a.gx, a.c, a.y, a.raw, a.pool_sum, a.pool_max,
-                                                          a.pool_last, a.lengths, a.step_done, a.T, a.ng, tiles, a.out_pad,
-                                                          a.kh_pad / 64, a.ldy, a.raw_ld, a.fast_math, a.trace);
+  if (a.tok != nullptr)  // layer 0 reading its input projection from the per-token table (api.cu, IE_EMB_PROJ)
+    lstm_wide_kernel<true><<<2 * pairs, kWThreads, smem, stream>>>(
+        a.tm_h, a.tm_w, a.gx, a.c, a.y, a.raw, a.pool_sum, a.pool_max, a.pool_last, a.lengths, a.step_done, a.T, a.ng, tiles,
+        a.out_pad, a.kh_pad / 64, a.ldy, a.raw_ld, a.fast_math, a.trace, a.tok);
+  else
+    lstm_wide_kernel<false><<<2 * pairs, kWThreads, smem, stream>>>(
+        a.tm_h, a.tm_w, a.gx, a.c, a.y, a.raw, a.pool_sum, a.pool_max, a.pool_last, a.lengths, a.step_done, a.T, a.ng, tiles,
+        a.out_pad, a.kh_pad / 64, a.ldy, a.raw_ld, a.fast_math, a.trace, nullptr);
   return cudaGetLastError();
 }
 

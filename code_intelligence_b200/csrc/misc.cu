@@ -70,6 +70,25 @@ __global__ void embed_gather_kernel(const int64_t* __restrict__ ids, int B, int 
   for (int i = lane; i < chunks; i += 32) dst[i] = __ldg(src + i);
 }
 
+// ids [B, T] int64 (batch-first) -> tok [T * b_pad] int32 (time-major, rows b >= B get the pad token), with the same
+// range check as embed_gather_kernel.  Used when layer 0 reads its input projection from the per-token table
+// (api.cu: IE_EMB_PROJ) instead of a GEMM over gathered embedding rows.
+__global__ void tokens_time_major_kernel(const int64_t* __restrict__ ids, int B, int T, int b_pad, int vocab, int pad_idx,
+                                         int* __restrict__ tok, int* err_flag) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(T) * b_pad;
+  if (i >= total) return;
+  const int t = static_cast<int>(i / b_pad);
+  const int b = static_cast<int>(i - static_cast<long long>(t) * b_pad);
+  long long id = pad_idx;
+  if (b < B) id = ids[static_cast<long long>(b) * T + t];
+  if (id < 0 || id >= vocab) {
+    atomicExch(err_flag, 1);
+    id = 0;
+  }
+  tok[i] = static_cast<int>(id);
+}
+
 __global__ void pool_finalize_kernel(const float* __restrict__ pool_sum, const float* __restrict__ pool_max,
                                      const float* __restrict__ pool_last, const int* __restrict__ lengths, int B, int e,
                                      int out_pad, float* __restrict__ out) {
@@ -117,6 +136,14 @@ cudaError_t launch_embed_gather(const int64_t* ids, int B, int T, int b_pad, con
   embed_gather_kernel<<<static_cast<unsigned>(blocks), wpb * 32, 0, stream>>>(
       ids, B, T, b_pad, reinterpret_cast<const uint4*>(emb), vocab, e_pad / 8, reinterpret_cast<uint4*>(x0), ldx / 8,
       pad_idx, err_flag);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_tokens_time_major(const int64_t* ids, int B, int T, int b_pad, int vocab, int pad_idx, int* tok,
+                                     int* err_flag, cudaStream_t stream) {
+  const long long total = static_cast<long long>(T) * b_pad;
+  const long long blocks = (total + 255) / 256;
+  tokens_time_major_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(ids, B, T, b_pad, vocab, pad_idx, tok, err_flag);
   return cudaGetLastError();
 }
 

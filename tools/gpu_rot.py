@@ -2,7 +2,7 @@
 csrc/lstm_rot.cu) against the default kernels of the same library -- the two must agree bit for bit, because every
 (row, unit) sees the same MMA tile shapes in the same K order -- and time both on the R4 encoder.
 
-    python tools/gpu_rot.py [--T 512] [--iters 3] [--skip-small] [--log gpurun_out/rot.jsonl]
+    python tools/gpu_rot.py [--T 512] [--iters 3] [--skip-small] [--proj] [--log gpurun_out/rot.jsonl]
 """
 import argparse
 import json
@@ -31,14 +31,17 @@ def rand_weights(n_layers, emb_sz, n_hid, vocab, seed=1234):
     return emb, layers
 
 
-def make(cfg, weights, rot):
+def make(cfg, weights, rot, proj=0):
+    """rot: IE_ROT value (0 = default kernels); proj: IE_EMB_PROJ (layer 0 from the per-token projection table)."""
     from code_intelligence_b200 import IssueEncoder
-    if rot:
-        os.environ["IE_ROT"] = str(rot)
-    else:
-        os.environ.pop("IE_ROT", None)
+    for k, v in (("IE_ROT", rot), ("IE_EMB_PROJ", proj)):
+        if v:
+            os.environ[k] = str(v)
+        else:
+            os.environ.pop(k, None)
     enc = IssueEncoder(*cfg, 1, 0).load_weights(*weights)
     os.environ.pop("IE_ROT", None)
+    os.environ.pop("IE_EMB_PROJ", None)
     return enc
 
 
@@ -52,25 +55,31 @@ def ids_lengths(B, T, vocab, seed, ragged=True):
     return ids, lengths
 
 
-def compare(name, cfg, weights, cases, log):
+def compare(name, cfg, weights, cases, log, proj=False):
     base = make(cfg, weights, 0)
     rot = make(cfg, weights, 2)
     assert rot.max_batch == 1280 and base.max_batch == 768, (rot.max_batch, base.max_batch)
+    others = {"rot": rot}
+    if proj:   # layer 0 from the per-token table, on the wide kernel (513..768 rows) and on the rotating kernel
+        others["wide+proj"] = make(cfg, weights, 0, proj=1)
+        others["rot+proj"] = make(cfg, weights, 2, proj=1)
     for (B, T) in cases:
         ids, lengths = ids_lengths(B, T, cfg[3], seed=B * 131 + T)
-        t0 = time.time()
         want = base.encode_ids(ids, lengths)
-        got = rot.encode_ids(ids, lengths)
-        rec = dict(check=name, B=B, T=T, equal=bool(np.array_equal(got, want)), finite=bool(np.isfinite(got).all()),
-                   max_abs=float(np.abs(got - want).max()), nbad_rows=int((np.abs(got - want).max(axis=1) > 0).sum()),
-                   sec=round(time.time() - t0, 2))
-        if B <= 768 and T <= 64:
-            raw_w, raw_g = base.raw_features(ids), rot.raw_features(ids)
-            rec["raw_equal"] = bool(np.array_equal(raw_w, raw_g))
-        print(json.dumps(rec), flush=True)
-        log.write(json.dumps(rec) + "\n")
-        log.flush()
-    return base, rot
+        for tag, enc in others.items():
+            if B > enc.max_batch:
+                continue
+            t0 = time.time()
+            got = enc.encode_ids(ids, lengths)
+            rec = dict(check=name, path=tag, B=B, T=T, equal=bool(np.array_equal(got, want)),
+                       finite=bool(np.isfinite(got).all()), max_abs=float(np.abs(got - want).max()),
+                       nbad_rows=int((np.abs(got - want).max(axis=1) > 0).sum()), sec=round(time.time() - t0, 2))
+            if B <= 768 and T <= 64:
+                rec["raw_equal"] = bool(np.array_equal(base.raw_features(ids), enc.raw_features(ids)))
+            print(json.dumps(rec), flush=True)
+            log.write(json.dumps(rec) + "\n")
+            log.flush()
+    return base, others
 
 
 def timeit(enc, B, T, vocab, iters):
@@ -99,16 +108,23 @@ def main():
     ap.add_argument("--T", type=int, default=512)
     ap.add_argument("--iters", type=int, default=3)
     ap.add_argument("--skip-small", action="store_true")
+    ap.add_argument("--only-small", action="store_true")
+    ap.add_argument("--proj", action="store_true", help="also check / time IE_EMB_PROJ=1 (layer 0 from the per-token table)")
     ap.add_argument("--log", default=os.path.join(ROOT, "gpurun_out", "rot.jsonl"))
     a = ap.parse_args()
     os.makedirs(os.path.dirname(a.log), exist_ok=True)
     log = open(a.log, "a")
     if not a.skip_small:
         cfg = (3, 96, 200, 500)
-        compare("small", cfg, rand_weights(*cfg), [(300, 19), (700, 23), (1100, 17), (1280, 9)], log)
+        compare("small", cfg, rand_weights(*cfg), [(300, 19), (700, 23), (1100, 17), (1280, 9)], log, a.proj)
+    if a.only_small:
+        return
     cfg = (4, 800, 2400, 60000)
-    base, rot = compare("r4", cfg, rand_weights(*cfg), [(768, 24), (1280, 40)], log)
-    for enc, B, tag in ((base, 768, "wide"), (rot, 1280, "rot5"), (rot, 768, "rot3")):
+    base, others = compare("r4", cfg, rand_weights(*cfg), [(768, 24), (1280, 40)], log, a.proj)
+    runs = [(base, 768, "wide"), (others["rot"], 1280, "rot5"), (others["rot"], 768, "rot3")]
+    if a.proj:
+        runs += [(others["wide+proj"], 768, "wide+proj"), (others["rot+proj"], 1280, "rot5+proj")]
+    for enc, B, tag in runs:
         rec = timeit(enc, B, a.T, cfg[3], a.iters)
         rec["path"] = tag
         print(json.dumps(rec), flush=True)
