@@ -107,6 +107,9 @@ struct ie_encoder {
   // GEMM from the same bf16 operands => the same bits) and the wide / rotating kernels read row tok[t, b] of it:
   // no embedding gather, no layer-0 GEMM, no Gx write for that layer.
   int use_proj = 0;
+  // experimental (IE_POOL_RAW=1): in wide / rotating calls the last layer writes its f32 h_t to `raw` and a separate
+  // kernel pools it (same sequential sums => same bits); the recurrent epilogue carries no pooling accumulators
+  int use_pool_raw = 0;
   bool proj_built = false;
   DevBuf proj, tok;
   DevBuf emb;  // bf16 [vocab, e_pad]
@@ -318,7 +321,8 @@ int run_encoder(ie_encoder* h, const int64_t* ids, const int32_t* lengths, int B
     return fail(IE_ERR_OOM, "B_pad*T = %lld tokens exceeds the workspace cap %lld; use a smaller batch",
                 static_cast<long long>(b_pad) * T, cap);
   CK(cudaSetDevice(c.device));
-  int rc = ensure_workspace(h, b_pad, T, raw_out != nullptr);
+  const bool pool_raw = h->use_pool_raw && pooled && raw_out == nullptr && (wide || rot);
+  int rc = ensure_workspace(h, b_pad, T, raw_out != nullptr || pool_raw);
   if (rc != IE_OK) return rc;
 
   // lengths: validate on the host when we can; padded rows get length 1
@@ -396,7 +400,7 @@ int run_encoder(ie_encoder* h, const int64_t* ids, const int32_t* lengths, int B
   // with three batches per launch the pooled last layer (narrow, latency bound) still runs the lstm_seq.cu kernel on its
   // plan-A layout when that is possible; all other layers use the wide tiles of plan B
   const Layer& lastA = h->layers.back();
-  const bool last_on_seq = wide && !rot && pooled && raw_out == nullptr && h->use_seq && lastA.u <= 12 && lastA.n_cta % 2 == 0 &&
+  const bool last_on_seq = wide && !rot && !pool_raw && pooled && raw_out == nullptr && h->use_seq && lastA.u <= 12 && lastA.n_cta % 2 == 0 &&
                            (c.n_layers < 2 || lastA.kin_pad == h->layersB[c.n_layers - 1].kin_pad);
   for (int l = 0; l < c.n_layers; ++l) {
     const bool last = (l == c.n_layers - 1);
@@ -438,8 +442,8 @@ int run_encoder(ie_encoder* h, const int64_t* ids, const int32_t* lengths, int B
     a.gx = from_table ? h->proj.as<float>() : h->gx.as<float>();
     a.c = h->c.as<float>();
     a.y = ybuf;
-    a.raw = (last && raw_out != nullptr) ? h->raw.as<float>() : nullptr;
-    a.pool_sum = (last && pooled) ? h->pool_sum.as<float>() : nullptr;
+    a.raw = (last && (raw_out != nullptr || pool_raw)) ? h->raw.as<float>() : nullptr;
+    a.pool_sum = (last && pooled && !pool_raw) ? h->pool_sum.as<float>() : nullptr;
     a.pool_max = h->pool_max.as<float>();
     a.pool_last = h->pool_last.as<float>();
     a.lengths = h->lengths.as<int>();
@@ -522,8 +526,11 @@ int run_encoder(ie_encoder* h, const int64_t* ids, const int32_t* lengths, int B
   const Layer& LL = (last_on_seq && !rot) ? h->layers.back() : LS.back();
   if (pooled) {
     float* out_dev = dev ? out : h->out.as<float>();
-    CK(ie::launch_pool_finalize(h->pool_sum.as<float>(), h->pool_max.as<float>(), h->pool_last.as<float>(),
-                                h->lengths.as<int>(), B, c.emb_sz, LL.out_pad, out_dev, s));
+    if (pool_raw)
+      CK(ie::launch_pool_from_raw(h->raw.as<float>(), h->lengths.as<int>(), B, T, c.emb_sz, LL.out_pad, out_dev, s));
+    else
+      CK(ie::launch_pool_finalize(h->pool_sum.as<float>(), h->pool_max.as<float>(), h->pool_last.as<float>(),
+                                  h->lengths.as<int>(), B, c.emb_sz, LL.out_pad, out_dev, s));
     h->launches++;
     if ((rc = mark(h, s)) != IE_OK) return rc;
     if (!dev)
@@ -577,6 +584,7 @@ int ie_encoder_create(const ie_config* cfg, ie_encoder** out) {
   if (const char* e = getenv("IE_SEQ")) h->use_seq = atoi(e);
   if (const char* e = getenv("IE_ROT")) h->use_rot = atoi(e);
   if (const char* e = getenv("IE_EMB_PROJ")) h->use_proj = atoi(e);
+  if (const char* e = getenv("IE_POOL_RAW")) h->use_pool_raw = atoi(e);
   if (h->use_rot) h->max_batch = 256 * ie::kRotMaxBatches;
   h->fast_math = (cfg->flags & IE_CFG_ACCURATE_GATES) ? 0 : 1;
   if (const char* e = getenv("IE_FAST_MATH")) h->fast_math = atoi(e);

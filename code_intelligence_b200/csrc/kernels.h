@@ -119,6 +119,9 @@ cudaError_t launch_tokens_time_major(const int64_t* ids, int B, int T, int b_pad
                                      int* err_flag, cudaStream_t stream);
 cudaError_t launch_pool_finalize(const float* pool_sum, const float* pool_max, const float* pool_last,
                                  const int* lengths, int B, int e, int out_pad, float* out, cudaStream_t stream);
+// same result from the last layer's f32 hidden states raw [.., T, raw_ld] (sequential over t: identical bits)
+cudaError_t launch_pool_from_raw(const float* raw, const int* lengths, int B, int T, int e, long long raw_ld, float* out,
+                                 cudaStream_t stream);
 // f32 [rows, cols] (row pitch ld_src) -> bf16 [rows_pad, ld_dst] with optional row permutation (src row of dst row r
 // = perm[r], or -1 for a zero row); columns >= cols zero filled.
 cudaError_t launch_convert_rows(const float* src, long long ld_src, int cols, const int* perm, int rows_dst,

@@ -104,6 +104,28 @@ __global__ void pool_finalize_kernel(const float* __restrict__ pool_sum, const f
   }
 }
 
+// Pooling from the last layer's f32 hidden states raw [b_pad, T, raw_ld] (written by the recurrent kernel): one thread per
+// (row, unit), t ascending -- the same sequential f32 sum, max and last as the in-kernel accumulators, so the same bits --
+// straight to out[b] = [sum/len | max | last].  (api.cu: IE_POOL_RAW)
+__global__ void pool_from_raw_kernel(const float* __restrict__ raw, const int* __restrict__ lengths, int T, int e,
+                                     long long raw_ld, float* __restrict__ out) {
+  const int b = blockIdx.x;
+  const int i = blockIdx.y * blockDim.x + threadIdx.x;
+  if (i >= e) return;
+  const int len = lengths[b];
+  const float* p = raw + static_cast<long long>(b) * T * raw_ld + i;
+  float s = p[0], m = s, last = s;
+  for (int t = 1; t < len; ++t) {
+    last = p[static_cast<long long>(t) * raw_ld];
+    s += last;
+    m = fmaxf(m, last);
+  }
+  float* o = out + static_cast<long long>(b) * 3 * e;
+  o[i] = s * (1.0f / static_cast<float>(len));
+  o[e + i] = m;
+  o[2 * e + i] = last;
+}
+
 __global__ void convert_rows_kernel(const float* __restrict__ src, long long ld_src, int cols, const int* __restrict__ perm,
                                     int rows_dst, __nv_bfloat16* __restrict__ dst, long long ld_dst) {
   const int r = blockIdx.x;
@@ -150,6 +172,13 @@ cudaError_t launch_tokens_time_major(const int64_t* ids, int B, int T, int b_pad
 cudaError_t launch_pool_finalize(const float* pool_sum, const float* pool_max, const float* pool_last,
                                  const int* lengths, int B, int e, int out_pad, float* out, cudaStream_t stream) {
   pool_finalize_kernel<<<B, 256, 0, stream>>>(pool_sum, pool_max, pool_last, lengths, B, e, out_pad, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pool_from_raw(const float* raw, const int* lengths, int B, int T, int e, long long raw_ld, float* out,
+                                 cudaStream_t stream) {
+  const dim3 grid(B, (e + 127) / 128);
+  pool_from_raw_kernel<<<grid, 128, 0, stream>>>(raw, lengths, T, e, raw_ld, out);
   return cudaGetLastError();
 }
 

@@ -2,7 +2,7 @@
 csrc/lstm_rot.cu) against the default kernels of the same library -- the two must agree bit for bit, because every
 (row, unit) sees the same MMA tile shapes in the same K order -- and time both on the R4 encoder.
 
-    python tools/gpu_rot.py [--T 512] [--iters 3] [--skip-small] [--proj] [--log gpurun_out/rot.jsonl]
+    python tools/gpu_rot.py [--T 512] [--iters 3] [--skip-small] [--proj] [--poolraw] [--log gpurun_out/rot.jsonl]
 """
 import argparse
 import json
@@ -31,18 +31,33 @@ def rand_weights(n_layers, emb_sz, n_hid, vocab, seed=1234):
     return emb, layers
 
 
-def make(cfg, weights, rot, proj=0):
-    """rot: IE_ROT value (0 = default kernels); proj: IE_EMB_PROJ (layer 0 from the per-token projection table)."""
+KNOBS = ("IE_ROT", "IE_EMB_PROJ", "IE_POOL_RAW")
+
+
+def make(cfg, weights, env=None):
+    """env: development knobs read at handle creation, e.g. {"IE_ROT": 2, "IE_EMB_PROJ": 1}."""
     from code_intelligence_b200 import IssueEncoder
-    for k, v in (("IE_ROT", rot), ("IE_EMB_PROJ", proj)):
-        if v:
-            os.environ[k] = str(v)
-        else:
-            os.environ.pop(k, None)
+    for k in KNOBS:
+        os.environ.pop(k, None)
+    for k, v in (env or {}).items():
+        os.environ[k] = str(v)
     enc = IssueEncoder(*cfg, 1, 0).load_weights(*weights)
-    os.environ.pop("IE_ROT", None)
-    os.environ.pop("IE_EMB_PROJ", None)
+    for k in KNOBS:
+        os.environ.pop(k, None)
     return enc
+
+
+def variants(a):
+    v = {"rot": {"IE_ROT": 2}}
+    if a.proj:     # layer 0 from the per-token table, on the wide kernel (513..768 rows) and on the rotating kernel
+        v["wide+proj"] = {"IE_EMB_PROJ": 1}
+        v["rot+proj"] = {"IE_ROT": 2, "IE_EMB_PROJ": 1}
+    if a.poolraw:  # last layer pooled from its f32 hidden states by a separate kernel
+        v["wide+poolraw"] = {"IE_POOL_RAW": 1}
+        v["rot+poolraw"] = {"IE_ROT": 2, "IE_POOL_RAW": 1}
+    if a.proj and a.poolraw:
+        v["rot+proj+poolraw"] = {"IE_ROT": 2, "IE_EMB_PROJ": 1, "IE_POOL_RAW": 1}
+    return v
 
 
 def ids_lengths(B, T, vocab, seed, ragged=True):
@@ -55,14 +70,10 @@ def ids_lengths(B, T, vocab, seed, ragged=True):
     return ids, lengths
 
 
-def compare(name, cfg, weights, cases, log, proj=False):
-    base = make(cfg, weights, 0)
-    rot = make(cfg, weights, 2)
-    assert rot.max_batch == 1280 and base.max_batch == 768, (rot.max_batch, base.max_batch)
-    others = {"rot": rot}
-    if proj:   # layer 0 from the per-token table, on the wide kernel (513..768 rows) and on the rotating kernel
-        others["wide+proj"] = make(cfg, weights, 0, proj=1)
-        others["rot+proj"] = make(cfg, weights, 2, proj=1)
+def compare(name, cfg, weights, cases, log, var):
+    base = make(cfg, weights)
+    others = {tag: make(cfg, weights, env) for tag, env in var.items()}
+    assert others["rot"].max_batch == 1280 and base.max_batch == 768, (others["rot"].max_batch, base.max_batch)
     for (B, T) in cases:
         ids, lengths = ids_lengths(B, T, cfg[3], seed=B * 131 + T)
         want = base.encode_ids(ids, lengths)
@@ -110,20 +121,22 @@ def main():
     ap.add_argument("--skip-small", action="store_true")
     ap.add_argument("--only-small", action="store_true")
     ap.add_argument("--proj", action="store_true", help="also check / time IE_EMB_PROJ=1 (layer 0 from the per-token table)")
+    ap.add_argument("--poolraw", action="store_true", help="also check / time IE_POOL_RAW=1 (pooling by a separate kernel)")
     ap.add_argument("--log", default=os.path.join(ROOT, "gpurun_out", "rot.jsonl"))
     a = ap.parse_args()
     os.makedirs(os.path.dirname(a.log), exist_ok=True)
     log = open(a.log, "a")
     if not a.skip_small:
         cfg = (3, 96, 200, 500)
-        compare("small", cfg, rand_weights(*cfg), [(300, 19), (700, 23), (1100, 17), (1280, 9)], log, a.proj)
+        compare("small", cfg, rand_weights(*cfg), [(300, 19), (700, 23), (1100, 17), (1280, 9)], log, variants(a))
     if a.only_small:
         return
     cfg = (4, 800, 2400, 60000)
-    base, others = compare("r4", cfg, rand_weights(*cfg), [(768, 24), (1280, 40)], log, a.proj)
+    base, others = compare("r4", cfg, rand_weights(*cfg), [(768, 24), (1280, 40)], log, variants(a))
     runs = [(base, 768, "wide"), (others["rot"], 1280, "rot5"), (others["rot"], 768, "rot3")]
-    if a.proj:
-        runs += [(others["wide+proj"], 768, "wide+proj"), (others["rot+proj"], 1280, "rot5+proj")]
+    for tag, enc in others.items():
+        if tag != "rot":
+            runs.append((enc, 1280 if tag.startswith("rot") else 768, tag + (" (1280 rows)" if tag.startswith("rot") else "")))
     for enc, B, tag in runs:
         rec = timeit(enc, B, a.T, cfg[3], a.iters)
         rec["path"] = tag
