@@ -224,3 +224,47 @@ def test_bench_clock_sampler_summary():
     assert s["sm_mhz"] == 1400.0 and s["sm_max_mhz"] == 1965.0 and s["reasons"] == ["sw_power_cap"]
     assert s["samples"] == 12 and s["samples_under_load"] == 7 and s["power_w"] == 990.1
     assert bench.ClockSampler.summarise([])["sm_mhz"] is None
+
+
+def _rot_schedule_model(T, ng, tiles, P, mma, lat, slots=2):
+    """Event model of csrc/lstm_rot.cu's schedule: item n = t*C + g*tiles + j (C = ng*tiles) runs on CTA pair n % P, pairs
+    walk their items in increasing n; an item's MMAs start when the pair is free, every item of (t-1, g) has been
+    published (its MMA end + lat) and the pair's item `slots` positions back has left its TMEM slot (MMA end + lat).
+    Returns (makespan, items seen, True if every dependency had a smaller index)."""
+    C, total = ng * tiles, T * ng * tiles
+    end, pub, cnt, tile_pub, pair_free = {}, {}, {}, {}, [0.0] * P
+    seen, ordered = set(), True
+    for n in range(total):                      # ascending n is a valid evaluation order iff deps have smaller indices
+        p, k = n % P, n // P
+        t, c = divmod(n, C)
+        g, j = divmod(c, tiles)
+        seen.add((t, g, j))
+        start = pair_free[p]
+        if t > 0:
+            if (t - 1, g) not in pub:           # some tile of (t-1, g) has an index >= n: the order argument would break
+                ordered = False
+                break
+            start = max(start, pub[(t - 1, g)])
+        if k >= slots:
+            start = max(start, end[n - slots * P] + lat)
+        end[n] = pair_free[p] = start + mma
+        tile_pub[(t, g)] = max(tile_pub.get((t, g), 0.0), end[n] + lat)
+        cnt[(t, g)] = cnt.get((t, g), 0) + 1
+        if cnt[(t, g)] == tiles:
+            pub[(t, g)] = tile_pub[(t, g)]
+    return (max(end.values()) + lat if end else 0.0), len(seen), ordered
+
+
+def test_rotating_schedule_model():
+    """Design claims of DESIGN.md section 4 / csrc/lstm_rot.cu, checked on a timing model: every (t, batch, tile) item is
+    dealt exactly once, an item only waits for smaller indices (=> no wait cycle for ANY pair count), and with five
+    batches at H = 2400 (C = 190 >= 2*74 + 38) the pairs issue back to back (within 2 % of 38*mma/74 per batch-step)
+    although each item's inputs take `lat` to become visible, while three batches leave that latency exposed."""
+    for (T, ng, tiles, P) in ((5, 1, 1, 74), (7, 3, 38, 74), (4, 5, 38, 74), (6, 5, 13, 74), (9, 2, 4, 3), (3, 5, 38, 1)):
+        span, n_items, ordered = _rot_schedule_model(T, ng, tiles, P, mma=1.0, lat=0.7)
+        assert ordered and n_items == T * ng * tiles and span > 0
+    mma, lat, T = 13.8, 8.0, 48
+    ideal = 38 * mma / 74
+    per_step = {ng: _rot_schedule_model(T, ng, 38, 74, mma, lat)[0] / T / ng for ng in (3, 5)}
+    assert per_step[5] <= 1.02 * ideal, per_step
+    assert per_step[3] >= 1.15 * ideal, per_step          # 114 items per timestep: the dependency latency shows
