@@ -585,7 +585,12 @@ int ie_encoder_create(const ie_config* cfg, ie_encoder** out) {
   if (const char* e = getenv("IE_ROT")) h->use_rot = atoi(e);
   if (const char* e = getenv("IE_EMB_PROJ")) h->use_proj = atoi(e);
   if (const char* e = getenv("IE_POOL_RAW")) h->use_pool_raw = atoi(e);
-  if (h->use_rot) h->max_batch = 256 * ie::kRotMaxBatches;
+  if (h->use_rot) {
+    // five batches put an item's inputs two rounds back (C = 190 >= 2*74 + 38); IE_ROT_BATCHES=6..8 buys more slack
+    int nb = 5;
+    if (const char* e = getenv("IE_ROT_BATCHES")) nb = std::min(ie::kRotMaxBatches, std::max(1, atoi(e)));
+    h->max_batch = std::max(IE_MAX_BATCH, 256 * nb);
+  }
   h->fast_math = (cfg->flags & IE_CFG_ACCURATE_GATES) ? 0 : 1;
   if (const char* e = getenv("IE_FAST_MATH")) h->fast_math = atoi(e);
   int rc = plan_layers(h, h->layers, 0);

@@ -101,7 +101,7 @@ cudaError_t launch_lstm_wide(const LstmWideArgs& a, cudaStream_t stream);
 
 // ---- persistent recurrent layer, rotating item schedule (lstm_rot.cu; experimental, IE_ROT=1): same arguments, up to
 //      kRotMaxBatches batches of 256 rows per launch; (timestep, batch, tile) items dealt round-robin over all CTA pairs
-constexpr int kRotMaxBatches = 5;
+constexpr int kRotMaxBatches = 8;  // compile-time bound; api.cu uses 5 per launch unless IE_ROT_BATCHES says otherwise
 cudaError_t launch_lstm_rot(const LstmWideArgs& a, cudaStream_t stream);
 int lstm_rot_pairs(const LstmWideArgs& a);  // CTA pairs the launch will use
 

@@ -96,9 +96,9 @@ int ie_encoder_raw_features(ie_encoder* h, const int64_t* ids, int32_t B, int32_
 /* Number of kernels this handle has launched so far (bench.py reports it as gpu_launches). */
 int64_t ie_encoder_launch_count(const ie_encoder* h);
 
-/* Rows one ie_encoder_encode call accepts on this handle: IE_MAX_BATCH, or 1280 (five 256-row batches per launch) when
- * the experimental rotating-schedule recurrent kernel was enabled with the environment variable IE_ROT=1 at create time
- * (csrc/lstm_rot.cu; off by default). */
+/* Rows one ie_encoder_encode call accepts on this handle: IE_MAX_BATCH, or 1280 (five 256-row batches per launch;
+ * IE_ROT_BATCHES=n, n <= 8, changes that to 256 n) when the experimental rotating-schedule recurrent kernel was enabled
+ * with the environment variable IE_ROT=1 at create time (csrc/lstm_rot.cu; off by default). */
 int32_t ie_encoder_max_batch(const ie_encoder* h);
 
 /* Device time of each phase of the last encode call on this handle, from CUDA events recorded on the launching
