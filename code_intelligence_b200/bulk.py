@@ -14,19 +14,26 @@ import numpy as np
 
 
 def encode_sorted_batches(docs: List[np.ndarray], encode_padded: Callable, pad_idx: int, out_dim: int, bs: int = 100,
-                          max_bs: int = 256, min_batches_rule: bool = True) -> np.ndarray:
+                          max_bs: int = 256, min_batches_rule: bool = True, coalesce: bool = False) -> np.ndarray:
     """The single-device bulk loop of ``df_to_embedding`` from the numericalised docs on
     (py/code_intelligence/inference.py:171-229): ``bs = min(bs, N//20 + 1)`` (at least 20 batches so that length
     sorting pays), argsort by length, batches of ``bs`` consecutive sorted docs right-padded to the batch's own max
     with ``pad_idx`` (pad_sequence, :207), ``encode_padded(ids[B,T], lengths[B]) -> (B, out_dim)``, on
     ``RuntimeError`` (CUDA OOM, :214-223) halve ``bs`` and retry the same position -- re-raised as ``Exception`` at
-    bs == 1 -- and finally unsort with argsort(argsort) (:226)."""
+    bs == 1 -- and finally unsort with argsort(argsort) (:226).
+
+    ``coalesce=True``: consecutive sorted batches are merged into device calls of ``max_bs`` rows.  On the B200 path a
+    row's result does not depend on its batch mates or on the padded length (bit-exact, tests/test_gpu_parity.py), so
+    ``bs`` -- a memory knob of the reference, default 100 -- only decides how many rows ride one launch; merging keeps
+    the results and lets a caller with the reference's default arguments reach the 768-row kernels."""
     n = len(docs)
     if n == 0:
         return np.empty((0, out_dim), dtype=np.float32)
     if min_batches_rule:
         bs = min(bs, (n // 20) + 1)
     bs = max(1, min(bs, max_bs))
+    if coalesce:
+        bs = max_bs
     length_arr = np.array([len(d) for d in docs])
     if (length_arr < 1).any():
         raise ValueError("empty token sequence")
@@ -47,7 +54,7 @@ def encode_sorted_batches(docs: List[np.ndarray], encode_padded: Callable, pad_i
         except RuntimeError as e:
             if bs == 1:
                 raise Exception(e)
-            bs = bs // 2
+            bs = max(1, min(bs, n - i) // 2)     # halve what was actually attempted (the tail may be shorter than bs)
     assert pooled.shape[0] == length_arr.shape[0]
     return pooled[len_mask_reversed, :]
 

@@ -162,11 +162,14 @@ class IssueEncoder:
                     finalize=v[1 + 2 * self.n_layers] if n > 1 + 2 * self.n_layers else 0.0)
 
     # ------------------------------------------------------------------ bulk (df_to_embedding on token ids)
-    def encode_id_list(self, docs: List[np.ndarray], bs: int = 100, min_batches_rule: bool = True) -> np.ndarray:
+    def encode_id_list(self, docs: List[np.ndarray], bs: int = 100, min_batches_rule: bool = True,
+                       coalesce: bool = True) -> np.ndarray:
         """The bulk loop of ``df_to_embedding`` (py/code_intelligence/inference.py:171-229) from the
         numericalised docs on: bs = min(bs, N//20+1), argsort by length, right-pad each batch to its own max
         with pad_idx, encode, unsort with argsort(argsort); on RuntimeError (CUDA OOM) halve bs and retry.
+        ``coalesce`` (default): consecutive sorted batches are merged into calls of ``max_batch`` rows -- results are
+        independent of batch composition here, so the reference's default ``bs=100`` still reaches the 768-row kernels.
         Returns (N, 3*emb_sz) float32 in input order."""
         from .bulk import encode_sorted_batches
         return encode_sorted_batches(docs, self.encode_ids, self.pad_idx, self.out_dim, bs=bs, max_bs=self.max_batch,
-                                     min_batches_rule=min_batches_rule)
+                                     min_batches_rule=min_batches_rule, coalesce=coalesce)

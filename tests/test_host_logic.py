@@ -268,3 +268,23 @@ def test_rotating_schedule_model():
     per_step = {ng: _rot_schedule_model(T, ng, 38, 74, mma, lat)[0] / T / ng for ng in (3, 5)}
     assert per_step[5] <= 1.02 * ideal, per_step
     assert per_step[3] >= 1.15 * ideal, per_step          # 114 items per timestep: the dependency latency shows
+
+
+def test_bulk_loop_coalesces_reference_batches():
+    """`coalesce=True` (the default of IssueEncoder.encode_id_list): the reference's bs (default 100) no longer decides
+    the device batch; consecutive sorted batches are merged into calls of max_bs rows, OOM halving still applies, and
+    the result equals the un-merged loop because a row's output is independent of its batch mates."""
+    enc = R.make_encoder(3, 400, 24, 40, 2)
+    docs = R.synthetic_ids(230, 20, seed=6, vocab_sz=400, min_len=1)
+    calls = []
+    def fn(ids, lengths):
+        calls.append(ids.shape)
+        if ids.shape[0] > 96:
+            raise RuntimeError("CUDA out of memory (simulated)")
+        return R.encode_padded(enc, ids, lengths)
+    want = bulk.encode_sorted_batches(docs, lambda i, l: R.encode_padded(enc, i, l), 1, 72, bs=10)
+    got = bulk.encode_sorted_batches(docs, fn, 1, 72, bs=10, max_bs=768, coalesce=True)
+    np.testing.assert_allclose(got, want, atol=1e-6)
+    assert [c[0] for c in calls[:3]] == [230, 115, 57]            # everything in one call, then halving until it fits
+    assert sum(c[0] for c in calls if c[0] <= 96) == 230
+    assert all(calls[i][1] <= calls[i + 1][1] for i in range(2, len(calls) - 1))
