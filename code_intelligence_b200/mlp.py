@@ -164,3 +164,14 @@ def filter_predictions(label_names: Sequence[str], probabilities: Sequence[float
     for l in labels_to_remove:
         del predictions[l]
     return predictions
+
+
+def calculate_auc(predictions, y_holdout, label_columns):
+    """Per-label ROC AUC and positive counts (py/label_microservice/mlp.py:140-160; evaluation helper of the training
+    notebooks, host-side sklearn).  Returns the DataFrame the reference ``display()``s."""
+    import pandas as pd
+    from sklearn.metrics import roc_auc_score
+    predictions, y_holdout = np.asarray(predictions), np.asarray(y_holdout)
+    auc_scores = [roc_auc_score(y_true=y_holdout[:, i], y_score=predictions[:, i]) for i, _ in enumerate(label_columns)]
+    counts = y_holdout.sum(axis=0)
+    return pd.DataFrame({'label': list(label_columns), 'auc': auc_scores, 'count': counts})
