@@ -11,7 +11,7 @@ dictionary of ``IssuesLoader`` / ``RepoMLP.load_training_data``.
 """
 from __future__ import annotations
 
-from typing import Dict, List, Sequence
+from typing import Dict, Sequence
 
 import numpy as np
 

@@ -8,12 +8,12 @@ and streams.
 from __future__ import annotations
 
 import ctypes as C
-from typing import List, Optional, Sequence
+from typing import List, Sequence
 
 import numpy as np
 
 from . import _lib
-from ._lib import IE_FLAG_DEVICE_PTRS, IE_MAX_BATCH, check, ie_config
+from ._lib import IE_FLAG_DEVICE_PTRS, check, ie_config
 
 
 def _layer_dims(n_layers, emb_sz, n_hid):
