@@ -288,3 +288,20 @@ def test_bulk_loop_coalesces_reference_batches():
     assert [c[0] for c in calls[:3]] == [230, 115, 57]            # everything in one call, then halving until it fits
     assert sum(c[0] for c in calls if c[0] <= 96) == 230
     assert all(calls[i][1] <= calls[i + 1][1] for i in range(2, len(calls) - 1))
+
+
+def test_c_abi_from_plain_c(tmp_path):
+    """The drop-in boundary is a C ABI: include/issue_emb_b200.h must compile as C99 (-pedantic -Werror), every declared
+    entry point must link from libissue_emb_b200.so, and without a GPU creation must fail with IE_ERR_CUDA and the
+    "no CPU fallback" message (tests/c_abi/abi_check.c)."""
+    import subprocess
+    from code_intelligence_b200 import _lib
+    _lib.load()                                            # builds the library if needed
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    exe = str(tmp_path / "abi_check")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "c_abi", "abi_check.c"), "-o", exe, "-L", libdir,
+                    "-l:" + os.path.basename(_lib.LIB_PATH), "-Wl,-rpath," + libdir], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "version=100 symbols=18" in r.stdout, r.stdout
