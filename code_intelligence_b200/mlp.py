@@ -100,25 +100,28 @@ class MLPWrapper:
         return self._head.predict_proba(X)
 
     def find_probability_thresholds(self, X, y, test_size=0.3):
-        """mlp.py:65-98: split, fit, then per label pick the threshold with the best precision among those meeting
-        both the precision and the recall threshold (None if there is none)."""
+        """mlp.py:65-98: hold out ``test_size`` of the data (random_state 1234), fit on the rest, and for every label keep
+        the probability threshold with the highest precision among the points of its precision-recall curve that meet
+        both ``precision_threshold`` and ``recall_threshold`` (first such point on ties; ``None`` when no point
+        qualifies, which makes the label unpredictable, repo_specific_model.py:138-141)."""
         from sklearn.metrics import precision_recall_curve
         from sklearn.model_selection import train_test_split
         X_train, X_test, y_train, y_test = train_test_split(X, y, test_size=test_size, random_state=1234)
         self.fit(X_train, y_train)
-        y_pred = self.predict_probabilities(X_test)
+        scores = self.predict_probabilities(X_test)
+        truth = np.asarray(y_test)
+        self.total_labels_count = truth.shape[1]
         self.probability_thresholds, self.precisions, self.recalls = {}, {}, {}
-        self.total_labels_count = len(y_test[0])
         for label in range(self.total_labels_count):
-            best_precision, best_recall, best_threshold = 0.0, 0.0, None
-            precision, recall, threshold = precision_recall_curve(np.array(y_test)[:, label], y_pred[:, label])
-            for prec, reca, thre in zip(precision[:-1], recall[:-1], threshold):
-                if prec >= self.precision_threshold and reca >= self.recall_threshold:
-                    if prec > best_precision:
-                        best_precision, best_recall, best_threshold = prec, reca, thre
-            self.probability_thresholds[label] = best_threshold
-            self.precisions[label] = best_precision
-            self.recalls[label] = best_recall
+            prec, rec, thr = precision_recall_curve(truth[:, label], scores[:, label])
+            prec, rec = prec[:-1], rec[:-1]                      # the curve's last point has no threshold
+            ok = (prec >= self.precision_threshold) & (rec >= self.recall_threshold) & (prec > 0.0)
+            if ok.any():
+                k = int(np.argmax(np.where(ok, prec, -1.0)))     # first index of the best qualifying precision
+                chosen = (thr[k], prec[k], rec[k])
+            else:
+                chosen = (None, 0.0, 0.0)
+            self.probability_thresholds[label], self.precisions[label], self.recalls[label] = chosen
 
     def grid_search(self, params=None, cv=5, n_jobs=-1):
         from sklearn.model_selection import GridSearchCV
