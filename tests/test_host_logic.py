@@ -305,3 +305,21 @@ def test_c_abi_from_plain_c(tmp_path):
     r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "version=100 symbols=18" in r.stdout, r.stdout
+
+
+def test_spacy_like_tokenizer_never_loses_characters():
+    """Property (hypothesis): for arbitrary text the splitter terminates and its tokens, concatenated, are the input with
+    only single separating spaces removed -- no character is dropped, duplicated or reordered."""
+    from hypothesis import given, settings, strategies as st
+    from code_intelligence_b200.tokenizer import SpacyLikeTokenizer
+    tok = SpacyLikeTokenizer(["xxbos", "xxmaj", "xxup"])
+    alphabet = st.sampled_from(list("abcXYZ019 .,;:!?'\"()[]{}<>-_/#@$%&*+=~`\n\t’“”…—") + ["n't", "'s", "...", "xxmaj", "e.g.", ":)"])
+
+    @settings(max_examples=300, deadline=None)
+    @given(st.lists(alphabet, max_size=40).map("".join))
+    def check(text):
+        toks = tok(text)
+        assert all(t != "" for t in toks)
+        assert "".join(toks).replace(" ", "") == text.replace(" ", "")
+
+    check()
