@@ -315,7 +315,7 @@ def test_spacy_like_tokenizer_never_loses_characters():
     tok = SpacyLikeTokenizer(["xxbos", "xxmaj", "xxup"])
     alphabet = st.sampled_from(list("abcXYZ019 .,;:!?'\"()[]{}<>-_/#@$%&*+=~`\n\t’“”…—") + ["n't", "'s", "...", "xxmaj", "e.g.", ":)"])
 
-    @settings(max_examples=300, deadline=None)
+    @settings(max_examples=300, deadline=None, derandomize=True)
     @given(st.lists(alphabet, max_size=40).map("".join))
     def check(text):
         toks = tok(text)
