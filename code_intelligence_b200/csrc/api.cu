@@ -100,7 +100,7 @@ struct ie_encoder {
   int use_wide = 1, wide_checked = 0;
   // experimental (IE_ROT=1): rotating item schedule (lstm_rot.cu), up to kRotMaxBatches batches per launch on plan B;
   // IE_ROT=2 also routes 256..768 rows through it (for testing).  max_batch is what ie_encoder_encode accepts.
-  int use_rot = 0, rot_checked = 0;
+  int use_rot = 0, rot_checked = 0, rot_variant = 0;  // rot_variant: IE_ROT_VARIANT (LstmWideArgs::variant)
   int max_batch = IE_MAX_BATCH;
   // experimental (IE_EMB_PROJ=1): layer 0's input projection W_ih0 . Emb[id] + b is a function of the token id alone,
   // so it is tabulated once per weight set (proj: [vocab_pad, 4*out_pad] f32, plan-B column order, computed by the same
@@ -304,7 +304,7 @@ int run_encoder(ie_encoder* h, const int64_t* ids, const int32_t* lengths, int B
     for (const Layer& L : h->layersB) {
       ie::LstmWideArgs q{};
       q.T = 1; q.ng = 1; q.u = L.u; q.n_cta = L.n_cta; q.out_pad = L.out_pad; q.kh_pad = L.kh_pad;
-      q.num_sms = h->num_sms; q.check_only = 1;
+      q.num_sms = h->num_sms; q.check_only = 1; q.variant = h->rot_variant;
       if (ie::launch_lstm_rot(q, s) != cudaSuccess) h->use_rot = 0;
     }
     cudaGetLastError();
@@ -463,6 +463,7 @@ int run_encoder(ie_encoder* h, const int64_t* ids, const int32_t* lengths, int B
       q.T = T; q.ng = b_pad / 256; q.u = L.u; q.n_cta = L.n_cta; q.out_pad = L.out_pad; q.kh_pad = L.kh_pad;
       q.ldy = a.ldy; q.raw_ld = a.raw_ld; q.fast_math = h->fast_math; q.num_sms = h->num_sms; q.check_only = 0;
       q.trace = nullptr;
+      q.variant = h->rot_variant;
       q.tok = from_table ? h->tok.as<int>() : nullptr;
       if (l == h->trace_layer) {
         const int pairs = ie::lstm_rot_pairs(q);
@@ -583,6 +584,7 @@ int ie_encoder_create(const ie_config* cfg, ie_encoder** out) {
   h->num_sms = sms;
   if (const char* e = getenv("IE_SEQ")) h->use_seq = atoi(e);
   if (const char* e = getenv("IE_ROT")) h->use_rot = atoi(e);
+  if (const char* e = getenv("IE_ROT_VARIANT")) h->rot_variant = atoi(e) & 3;
   if (const char* e = getenv("IE_EMB_PROJ")) h->use_proj = atoi(e);
   if (const char* e = getenv("IE_POOL_RAW")) h->use_pool_raw = atoi(e);
   if (h->use_rot) {

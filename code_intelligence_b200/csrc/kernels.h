@@ -94,6 +94,7 @@ struct LstmWideArgs {
   int fast_math, num_sms, check_only;
   long long* trace;  // optional [grid][T][12] timeline (debug)
   int trace_items;   // lstm_rot.cu only: the timeline is [grid][trace_items][12], one record per work item of the pair
+  int variant;       // lstm_rot.cu only (IE_ROT_VARIANT): bit 0 proxy fence in the watcher warp, bit 1 four-stage h ring
   const int* tok;    // optional [T*256*ng] time-major token ids: Gx row of (t, row) is gx[tok[t*b_pad+row]] (per-token
                      // input-projection table of layer 0, api.cu IE_EMB_PROJ) instead of gx[t*b_pad+row]
 };

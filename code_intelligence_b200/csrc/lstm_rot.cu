@@ -34,7 +34,7 @@ namespace ie {
 namespace {
 
 constexpr int kRThreads = 640;  // 4 role warps + 16 epilogue warps (4 per TMEM lane quarter, 64 columns each)
-constexpr int kRGA = 2, kRAStages = 3;  // h ring: 3 stages x 2 k-blocks x 16 KB
+constexpr int kRGA = 2;                 // h ring: AST (3, variant: 4) stages x 2 k-blocks x 16 KB
 constexpr int kRGW = 2, kRWStages = 3;  // W ring: 3 stages x 2 k-blocks x 16 KB
 constexpr int kRTileN = 256;            // accumulator columns per tile = 64 hidden units
 constexpr int kRHalfRows = 128;         // W rows each CTA of the pair contributes
@@ -58,7 +58,10 @@ __device__ __forceinline__ void wait_seq_ge(const uint32_t* p, uint32_t target) 
   }
 }
 
-template <bool TOK>
+// TOK: Gx rows indexed by token id (per-token projection table).  Variant knobs for round-2 experiments (both ran in
+// the r7 session with identical results): WFENCE = the watcher, not the TMA-issuing thread, executes fence.proxy.async;
+// AST = stages of the h ring.  <*, false, 3> is the validated default.
+template <bool TOK, bool WFENCE, int AST>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kRThreads, 1)
 lstm_rot_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ CUtensorMap tm_w,
                 const float* __restrict__ gx, float* cstate, __nv_bfloat16* __restrict__ y, float* __restrict__ raw,
@@ -73,11 +76,11 @@ lstm_rot_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
   constexpr uint32_t a_bytes = 128 * 64 * 2;
   constexpr uint32_t w_bytes = kRHalfRows * 64 * 2;
   uint8_t* a_ring = smem;
-  uint8_t* w_ring = smem + kRAStages * kRGA * a_bytes;
+  uint8_t* w_ring = smem + AST * kRGA * a_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(w_ring + kRWStages * kRGW * w_bytes);
-  uint64_t* afull = bars;                   // [kRAStages] leader's copy is live
-  uint64_t* aempty = afull + kRAStages;
-  uint64_t* wfull = aempty + kRAStages;     // [kRWStages]
+  uint64_t* afull = bars;                   // [AST] leader's copy is live
+  uint64_t* aempty = afull + AST;
+  uint64_t* wfull = aempty + AST;     // [kRWStages]
   uint64_t* wempty = wfull + kRWStages;
   uint64_t* tfull = wempty + kRWStages;     // [2] accumulator slot holds a finished item (both CTAs' copies live)
   uint64_t* tempty = tfull + 2;             // [2] accumulator slot drained by both CTAs (leader's copy is live)
@@ -105,7 +108,7 @@ lstm_rot_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
     tma_prefetch_desc(&tm_w);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < kRAStages; ++s) {
+    for (int s = 0; s < AST; ++s) {
       mbar_init(&afull[s], 2);
       mbar_init(&aempty[s], 1);
     }
@@ -137,7 +140,7 @@ lstm_rot_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
         const int t = static_cast<int>(n / C);
         const int g = static_cast<int>(n - static_cast<long long>(t) * C) / tiles;
         wait_seq_ge(cready, static_cast<uint32_t>(k + 1));  // the watcher (warp 2) has seen counter (t-1, g)
-        if (t > 0) fence_proxy_async();  // h_{t-1} was written through the generic proxy, TMA reads it
+        if (!WFENCE && t > 0) fence_proxy_async();  // h_{t-1} was written through the generic proxy, TMA reads it
         IE_TRACE(0, k);
         const int row0 = t * b_pad + g * 256 + static_cast<int>(crank) * 128;
         for (int kb0 = 0; kb0 < num_k_blocks; kb0 += kRGA) {
@@ -148,7 +151,7 @@ lstm_rot_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
           for (int q = 0; q < nb; ++q)
             tma_load_2d_pair(a_ring + (stage * kRGA + q) * a_bytes, &tm_h, &afull[stage], (kb0 + q) * 64, row0,
                              kEvictNormal);
-          if (++stage == kRAStages) { stage = 0; phase ^= 1; }
+          if (++stage == AST) { stage = 0; phase ^= 1; }
         }
         IE_TRACE(1, k);
       }
@@ -163,7 +166,10 @@ lstm_rot_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
       for (long long n = pair; n < total; n += P, ++k) {
         const int t = static_cast<int>(n / C);
         const int g = static_cast<int>(n - static_cast<long long>(t) * C) / tiles;
-        if (t > 0) wait_flag_ge_relaxed(step_done + (t - 1) * ng + g, batch_ctas);  // ends with a gpu-scope fence
+        if (t > 0) {
+          wait_flag_ge_relaxed(step_done + (t - 1) * ng + g, batch_ctas);  // ends with a gpu-scope fence
+          if (WFENCE) fence_proxy_async();
+        }
         st_release_cta(cready, static_cast<uint32_t>(k + 1));
       }
     }
@@ -226,7 +232,7 @@ lstm_rot_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
           const bool last = (kb == num_k_blocks - 1);
           if (ja == kRGA - 1 || last) {
             umma_commit_pair_mc(&aempty[as], 0x3);
-            if (++as == kRAStages) { as = 0; aph ^= 1; }
+            if (++as == AST) { as = 0; aph ^= 1; }
           }
           if (jw == kRGW - 1 || last) {
             umma_commit_pair_mc(&wempty[ws], 0x3);
@@ -352,9 +358,36 @@ lstm_rot_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant_
 #undef IE_TRACE_VAL
 }
 
-size_t rot_smem_bytes() {
-  return 1024 + static_cast<size_t>(kRAStages) * kRGA * 128 * 64 * 2 + static_cast<size_t>(kRWStages) * kRGW * kRHalfRows * 64 * 2 +
-         (2 * kRAStages + 2 * kRWStages + 4) * 8 + 16;
+size_t rot_smem_bytes(int ast) {
+  return 1024 + static_cast<size_t>(ast) * kRGA * 128 * 64 * 2 + static_cast<size_t>(kRWStages) * kRGW * kRHalfRows * 64 * 2 +
+         (2 * ast + 2 * kRWStages + 4) * 8 + 16;
+}
+
+template <bool TOK, bool WFENCE, int AST>
+cudaError_t launch_rot_t(const LstmWideArgs& a, int pairs, int tiles, cudaStream_t stream) {
+  auto kfn = lstm_rot_kernel<TOK, WFENCE, AST>;
+  const size_t smem = rot_smem_bytes(AST);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  if (a.check_only) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * (a.num_sms / 2));
+    cfg.blockDim = dim3(kRThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    int max_clusters = 0;
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&max_clusters, kfn, &cfg);
+    if (e != cudaSuccess) return e;
+    return max_clusters >= a.num_sms / 2 ? cudaSuccess : cudaErrorCooperativeLaunchTooLarge;
+  }
+  kfn<<<2 * pairs, kRThreads, smem, stream>>>(a.tm_h, a.tm_w, a.gx, a.c, a.y, a.raw, a.pool_sum, a.pool_max, a.pool_last,
+                                               a.lengths, a.step_done, a.T, a.ng, tiles, a.out_pad, a.kh_pad / 64, a.ldy,
+                                               a.raw_ld, a.fast_math, a.trace, a.trace_items, a.tok);
+  return cudaGetLastError();
 }
 
 }  // namespace
@@ -367,40 +400,19 @@ int lstm_rot_pairs(const LstmWideArgs& a) {
 }
 
 // a.check_only: only verify co-residency of the grid.  Requires u == 32 per CTA (64 units per pair tile).
+// a.variant (round-2 experiments, IE_ROT_VARIANT): bit 0 = proxy fence in the watcher warp, bit 1 = 4-stage h ring.
 cudaError_t launch_lstm_rot(const LstmWideArgs& a, cudaStream_t stream) {
   if (a.u != 32 || a.n_cta % 2 || a.kh_pad % 64 || a.ng < 1 || a.ng > kRotMaxBatches || a.T < 1) return cudaErrorInvalidValue;
   const int tiles = a.n_cta / 2;
   const int pairs = lstm_rot_pairs(a);
   if (pairs < 1) return cudaErrorInvalidValue;
-  const size_t smem = rot_smem_bytes();
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(lstm_rot_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(lstm_rot_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
+  const bool tok = a.tok != nullptr;  // layer 0 reading its input projection from the per-token table (IE_EMB_PROJ)
+  switch (a.variant & 3) {
+    case 0: return tok ? launch_rot_t<true, false, 3>(a, pairs, tiles, stream) : launch_rot_t<false, false, 3>(a, pairs, tiles, stream);
+    case 1: return tok ? launch_rot_t<true, true, 3>(a, pairs, tiles, stream) : launch_rot_t<false, true, 3>(a, pairs, tiles, stream);
+    case 2: return tok ? launch_rot_t<true, false, 4>(a, pairs, tiles, stream) : launch_rot_t<false, false, 4>(a, pairs, tiles, stream);
+    default: return tok ? launch_rot_t<true, true, 4>(a, pairs, tiles, stream) : launch_rot_t<false, true, 4>(a, pairs, tiles, stream);
   }
-  if (a.check_only) {
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(2 * (a.num_sms / 2));
-    cfg.blockDim = dim3(kRThreads);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = stream;
-    int max_clusters = 0;
-    cudaError_t e = cudaOccupancyMaxActiveClusters(&max_clusters, lstm_rot_kernel<false>, &cfg);
-    if (e != cudaSuccess) return e;
-    return max_clusters >= a.num_sms / 2 ? cudaSuccess : cudaErrorCooperativeLaunchTooLarge;
-  }
-  if (a.tok != nullptr)  // layer 0 reading its input projection from the per-token table (api.cu, IE_EMB_PROJ)
-    lstm_rot_kernel<true><<<2 * pairs, kRThreads, smem, stream>>>(
-        a.tm_h, a.tm_w, a.gx, a.c, a.y, a.raw, a.pool_sum, a.pool_max, a.pool_last, a.lengths, a.step_done, a.T, a.ng, tiles,
-        a.out_pad, a.kh_pad / 64, a.ldy, a.raw_ld, a.fast_math, a.trace, a.trace_items, a.tok);
-  else
-    lstm_rot_kernel<false><<<2 * pairs, kRThreads, smem, stream>>>(
-        a.tm_h, a.tm_w, a.gx, a.c, a.y, a.raw, a.pool_sum, a.pool_max, a.pool_last, a.lengths, a.step_done, a.T, a.ng, tiles,
-        a.out_pad, a.kh_pad / 64, a.ldy, a.raw_ld, a.fast_math, a.trace, a.trace_items, nullptr);
-  return cudaGetLastError();
 }
 
 }  // namespace ie

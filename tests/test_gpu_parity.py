@@ -219,7 +219,9 @@ def test_rotating_schedule_kernel_matches_default(monkeypatch):
                     reason="opt-in development knobs not yet validated at full size; run with IE_TEST_EXPERIMENTAL=1")
 @pytest.mark.parametrize("knobs", [{"IE_EMB_PROJ": "1"}, {"IE_ROT": "2", "IE_EMB_PROJ": "1"}, {"IE_POOL_RAW": "1"},
                                    {"IE_ROT": "2", "IE_POOL_RAW": "1"}, {"IE_ROT": "2", "IE_ROT_BATCHES": "6"},
-                                   {"IE_ROT": "2", "IE_EMB_PROJ": "1", "IE_POOL_RAW": "1", "IE_ROT_BATCHES": "8"}])
+                                   {"IE_ROT": "2", "IE_EMB_PROJ": "1", "IE_POOL_RAW": "1", "IE_ROT_BATCHES": "8"},
+                                   {"IE_ROT": "2", "IE_ROT_VARIANT": "1"}, {"IE_ROT": "2", "IE_ROT_VARIANT": "2"},
+                                   {"IE_ROT": "2", "IE_ROT_VARIANT": "3", "IE_ROT_BATCHES": "6"}])
 def test_experimental_knobs_match_default(knobs, monkeypatch):
     """DESIGN.md section 4 "Development knobs": every opt-in path must reproduce the default kernels bit for bit
     (per-token projection table = the same GEMM on the same operands; pooling from the f32 hidden states = the same
@@ -227,7 +229,7 @@ def test_experimental_knobs_match_default(knobs, monkeypatch):
     from code_intelligence_b200 import IssueEncoder
     n_layers, emb_sz, n_hid, vocab = 3, 96, 200, 500
     emb, layers = R.make_encoder(7, vocab, emb_sz, n_hid, n_layers).export_weights()
-    for k in ("IE_ROT", "IE_ROT_BATCHES", "IE_EMB_PROJ", "IE_POOL_RAW"):
+    for k in ("IE_ROT", "IE_ROT_BATCHES", "IE_ROT_VARIANT", "IE_EMB_PROJ", "IE_POOL_RAW"):
         monkeypatch.delenv(k, raising=False)
     base = IssueEncoder(n_layers, emb_sz, n_hid, vocab).load_weights(emb, layers)
     for k, v in knobs.items():

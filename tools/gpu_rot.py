@@ -2,7 +2,7 @@
 csrc/lstm_rot.cu) against the default kernels of the same library -- the two must agree bit for bit, because every
 (row, unit) sees the same MMA tile shapes in the same K order -- and time both on the R4 encoder.
 
-    python tools/gpu_rot.py [--T 512] [--iters 3] [--skip-small] [--proj] [--poolraw] [--log gpurun_out/rot.jsonl]
+    python tools/gpu_rot.py [--T 512] [--iters 3] [--skip-small] [--proj] [--poolraw] [--rotvar] [--log gpurun_out/rot.jsonl]
 """
 import argparse
 import json
@@ -31,7 +31,7 @@ def rand_weights(n_layers, emb_sz, n_hid, vocab, seed=1234):
     return emb, layers
 
 
-KNOBS = ("IE_ROT", "IE_EMB_PROJ", "IE_POOL_RAW")
+KNOBS = ("IE_ROT", "IE_ROT_BATCHES", "IE_ROT_VARIANT", "IE_EMB_PROJ", "IE_POOL_RAW")
 
 
 def make(cfg, weights, env=None):
@@ -57,6 +57,11 @@ def variants(a):
         v["rot+poolraw"] = {"IE_ROT": 2, "IE_POOL_RAW": 1}
     if a.proj and a.poolraw:
         v["rot+proj+poolraw"] = {"IE_ROT": 2, "IE_EMB_PROJ": 1, "IE_POOL_RAW": 1}
+    if a.rotvar:   # kernel variants (IE_ROT_VARIANT: 1 = proxy fence in the watcher, 2 = 4-stage h ring, 3 = both), 6 batches
+        for var in (1, 2, 3):
+            v[f"rot.v{var}"] = {"IE_ROT": 2, "IE_ROT_VARIANT": var}
+        v["rot.b6"] = {"IE_ROT": 2, "IE_ROT_BATCHES": 6}
+        v["rot.b6.v1"] = {"IE_ROT": 2, "IE_ROT_BATCHES": 6, "IE_ROT_VARIANT": 1}
     return v
 
 
@@ -122,6 +127,7 @@ def main():
     ap.add_argument("--only-small", action="store_true")
     ap.add_argument("--proj", action="store_true", help="also check / time IE_EMB_PROJ=1 (layer 0 from the per-token table)")
     ap.add_argument("--poolraw", action="store_true", help="also check / time IE_POOL_RAW=1 (pooling by a separate kernel)")
+    ap.add_argument("--rotvar", action="store_true", help="also check / time IE_ROT_VARIANT=1..3 and IE_ROT_BATCHES=6")
     ap.add_argument("--log", default=os.path.join(ROOT, "gpurun_out", "rot.jsonl"))
     a = ap.parse_args()
     os.makedirs(os.path.dirname(a.log), exist_ok=True)
@@ -136,7 +142,8 @@ def main():
     runs = [(base, 768, "wide"), (others["rot"], 1280, "rot5"), (others["rot"], 768, "rot3")]
     for tag, enc in others.items():
         if tag != "rot":
-            runs.append((enc, 1280 if tag.startswith("rot") else 768, tag + (" (1280 rows)" if tag.startswith("rot") else "")))
+            rows = enc.max_batch if tag.startswith("rot") else 768
+            runs.append((enc, rows, f"{tag} ({rows} rows)"))
     for enc, B, tag in runs:
         rec = timeit(enc, B, a.T, cfg[3], a.iters)
         rec["path"] = tag
