@@ -144,12 +144,14 @@ def main():
         if tag != "rot":
             rows = enc.max_batch if tag.startswith("rot") else 768
             runs.append((enc, rows, f"{tag} ({rows} rows)"))
-    for enc, B, tag in runs:
+    for i, (enc, B, tag) in enumerate(runs):
         rec = timeit(enc, B, a.T, cfg[3], a.iters)
         rec["path"] = tag
         print(json.dumps(rec), flush=True)
         log.write(json.dumps(rec) + "\n")
         log.flush()
+        if all(e is not enc for e, _, _ in runs[i + 1:]):
+            enc.close()        # full-size workspaces are 20-45 GB each: free them as we go
 
 
 if __name__ == "__main__":
