@@ -323,3 +323,12 @@ def test_spacy_like_tokenizer_never_loses_characters():
         assert "".join(toks).replace(" ", "") == text.replace(" ", "")
 
     check()
+
+
+def test_filter_predictions_reference_case():
+    """The reference's own test of the label filter (py/label_microservice/repo_specific_model_test.py:10-33): mocked
+    probabilities [[.2, .9]] with thresholds .5 / .5 give {"label2": .9}; a falsy threshold removes the label."""
+    from code_intelligence_b200.mlp import filter_predictions
+    assert filter_predictions(["label1", "label2"], [.2, .9], {"label1": .5, "label2": .5}) == {"label2": .9}
+    assert filter_predictions(["a", "b", "c"], [.9, .9, .4], {"a": None, "b": 0, "c": .3}) == {"c": .4}
+    assert filter_predictions([], [], {}) == {}
