@@ -74,10 +74,45 @@ def mlp_fixture():
         print('mlp', tag, probs.shape, float(probs.mean()))
 
 
-if __name__ == '__main__':
+if __name__ == '__main__' and len(sys.argv) == 1:
     encoder_fixture('encoder_tiny.npz', 2, 64, 128, 1000, 5, 9, 2, seed=11)
     encoder_fixture('encoder_pad_dims.npz', 3, 50, 70, 300, 7, 12, 1, seed=12, scale=2.0)   # dims that need padding
     encoder_fixture('encoder_r4.npz', 4, 800, 2400, 60000, 32, 128, None, seed=1234, with_weights=False)  # config 1
     encoder_fixture('encoder_r4_varlen.npz', 4, 800, 2400, 60000, 24, 96, 5, seed=1234, scale=3.0, with_weights=False)
     encoder_fixture('encoder_n3.npz', 3, 800, 2400, 60000, 16, 64, 8, seed=1234, with_weights=False)
     mlp_fixture()
+
+
+def full_size_fixture(name, n_layers, rows, T, seed, scale=1.0):
+    """Reference-shape fixtures at the shapes bench.py / the sweep measure (weights re-derived from the seed).
+    rows: list of (count, min_len) groups; min_len None = fixed length T.  Stored compactly: int32 ids, f32 outputs,
+    plus the f64 per-row L2 norm of the oracle output (cheap sanity value for the loader)."""
+    torch.set_num_threads(os.cpu_count())
+    enc = R.make_encoder(seed, 60000, 800, 2400, n_layers, scale=scale)
+    docs = []
+    for gi, (cnt, min_len) in enumerate(rows):
+        docs += R.synthetic_ids(cnt, T, seed=seed + 101 + gi, vocab_sz=60000, min_len=min_len)
+    ids, lengths = padded(docs, T)
+    outs = []
+    step = 64
+    for b0 in range(0, len(docs), step):            # bounded host memory: (64, T, 2400) f32 activations per call
+        tt = int(lengths[b0:b0 + step].max())
+        outs.append(R.encode_padded(enc, ids[b0:b0 + step, :tt], lengths[b0:b0 + step]))
+    out = np.concatenate(outs).astype(np.float32)
+    np.savez_compressed(os.path.join(HERE, name), cfg=np.array([n_layers, 800, 2400, 60000, seed], dtype=np.int64),
+                        scale=np.float64(scale), ids=ids.astype(np.int32), lengths=lengths, expected=out)
+    print(name, out.shape, float(np.abs(out).mean()), flush=True)
+
+
+def full_size():
+    # bench shape (BASELINE configs[1]): 256 x 512; rows 0..127 full length, rows 128..255 var-len in [64, 512]
+    full_size_fixture('encoder_r4_b256_t512.npz', 4, [(128, None), (128, 64)], 512, seed=1234)
+    # sweep buckets (configs[2]): lengths in (T/2, T]
+    full_size_fixture('encoder_r4_t1024.npz', 4, [(32, 513)], 1024, seed=1234)
+    full_size_fixture('encoder_r4_t2048.npz', 4, [(32, 1025)], 2048, seed=1234)
+    # the north star's literal 3-layer shape
+    full_size_fixture('encoder_n3_b64_t512.npz', 3, [(32, None), (32, 32)], 512, seed=1234)
+
+
+if __name__ == '__main__' and len(sys.argv) > 1 and sys.argv[1] == 'full':
+    full_size()
