@@ -4,29 +4,36 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
 
 One "step" = one pass of the hot path over one batch of 256 synthetic issues x 512 tokens (BASELINE.json configs[1]
-shape; reference-deployed R4 encoder: L=4, E=800, H=2400, V=60000, random-init seed 1234): embedding gather, 4 hoisted
-input-projection GEMMs, 4 x 512 recurrent LSTM steps, masked [mean|max|last] pool -> (256, 2400) f32.
+shape; reference-deployed R4 encoder: L=4, E=800, H=2400, V=60000, random-init seed 1234): token ids -> per-token
+input-projection table lookup (layer 0) / hoisted input-projection GEMMs (layers 1-3) -> 4 x 512 recurrent LSTM steps
+-> masked [mean|max|last] pool -> (256, 2400) f32.
 
-Three consecutive steps (three batches of 256) ride one launch of the persistent recurrent kernels (ie_encoder_encode with
-768 rows = IE_MAX_BATCH): the (batch, column-tile) MMA chains of the three batches are dealt over all 74 CTA pairs, and
-while one batch is in its epilogue / step barrier the tensor pipe works on another.  Each step is still one batch of
-256 issues with its own result rows; `single_batch` in the JSON line is the same measurement with one batch per launch.
+`batches_per_launch` (5) consecutive steps ride one ie_encoder_encode call (1280 rows): the persistent recurrent kernel
+(csrc/lstm_layer.cu) deals the (timestep, batch, column-tile) work items of the five independent batches round-robin over
+all 74 CTA pairs, so an item's inputs were finished two rounds earlier and the tensor pipe never waits for a step
+barrier.  Each step is still one batch of 256 issues with its own result rows; `single_batch` in the JSON line is the
+same measurement with one batch per launch.
 
 * `value`      : whole-job issues/s with the token ids already resident in HBM (CUDA events on the launching stream,
                  barrier + synchronize on both sides, max over ranks; under torchrun each rank encodes its own batches
                  -- weak scaling, no data-path collective -- and the timed region ends with the ONE all-gather of the
                  2400-d outputs).
-* `e2e`        : the same metric through the public host-buffer API (IssueEncoder.encode_ids == C-ABI ie_encoder_encode
-                 with pinned host ids/lengths/out): H2D of ids+lengths and D2H of the (256,2400) result inside the
-                 timed region, every step.
-* `roofline`   : dominant kernel = lstm_step_kernel (the recurrent h_{t-1} W_hh^T + gates step of the 2400-wide
-                 layers).  achieved = algorithmic FLOPs per launch (2*256*2400*9600 = 11.8 GFLOP) / average launch
-                 duration, the latter from CUDA events recorded inside ie_encoder_encode around the 512 launches of each
-                 layer (ie_encoder_last_phase_ms).  peak = MEASURED_PEAKS.json bf16_tflops_sustained.
+* `e2e`        : the same metric through the public bulk API on HOST token-id lists -- what df_to_embedding does after
+                 tokenisation (py/code_intelligence/inference.py:171-229): bulk.encode_bulk_distributed(docs, ...) = global
+                 length sort -> issue j to rank j mod G -> IssueEncoder.encode_id_list pipeline (pinned staging, H2D under
+                 the previous batch's kernels, C-ABI ie_encoder_encode) -> one NCCL all-gather -> un-sort -> D2H of the
+                 (N, 2400) result.  Host packing, H2D, D2H are all inside the timed region (perf_counter around the call,
+                 device idle before, max over ranks).
+* `roofline`   : dominant kernel = lstm_layer_kernel on the 2400-wide layers.  achieved = algorithmic FLOPs per launch
+                 (2*256*2400*9600 per batch-step x 512 steps x batches in the launch) / launch duration from CUDA events
+                 recorded inside ie_encoder_encode around it (ie_encoder_last_phase_ms; average of the three 2400-wide
+                 layers of the last timed call).  peak = MEASURED_PEAKS.json bf16_tflops_sustained.
 * `cpu_baseline`: the CPU oracle (oracle/awd_lstm_ref.py, torch nn.LSTM fp32 == the modules the reference's fastai
-                 model wraps) timed on this box's host cores on a bounded sample.
+                 model wraps) timed on this box's host cores on a bounded sample (>= 32 issues).
 * `--impl reference`: times that CPU path alone (the reference's own encoder is not installable: fastai/spaCy absent,
-                 no network -- see DESIGN.md); each step is a bounded sample of the same workload.
+                 no network -- see DESIGN.md); each step is a bounded sample (>= 32 issues) of the same workload.
+* `extra`      : fp32-accurate mode (IE_CFG_FP32), the north star's literal 3-layer shape (N3), the device-resident MLP
+                 head (configs[4]) and a var-len bulk run checked bit for bit against a single-GPU encode.
 """
 import argparse
 import json
@@ -41,7 +48,14 @@ sys.path.insert(0, ROOT)
 
 B, T = 256, 512
 N_LAYERS, EMB, HID, VOCAB = 4, 800, 2400, 60000
-FLOP_PER_TOKEN = 2 * sum(4 * o * (i + o) for i, o in [(800, 2400), (2400, 2400), (2400, 2400), (2400, 800)])  # 266.24e6
+
+
+def flop_per_token(n_layers=N_LAYERS):
+    dims = [((EMB if l == 0 else HID), (HID if l != n_layers - 1 else EMB)) for l in range(n_layers)]
+    return 2 * sum(4 * o * (i + o) for i, o in dims)     # R4: 266.24e6, N3: 174.08e6
+
+
+FLOP_PER_TOKEN = flop_per_token()
 STEP_FLOP_2400 = 2.0 * B * 2400 * 9600   # one recurrent step of one 2400-wide layer, one batch of 256
 
 
@@ -125,37 +139,43 @@ def usable_cpus():
     return max(1, n)
 
 
+CPU_SAMPLE_MIN = 32   # issues per CPU sample: fewer under-feed the BLAS threads (round-1 verdict: 7 issues -> 2x too slow)
+
+
 def cpu_oracle_setup():
     """Build the CPU oracle encoder and pick the torch thread count that maximises its throughput on this box
-    (more threads than usable cores, or than the small per-step GEMMs can feed, makes it slower)."""
+    (more threads than usable cores makes it slower).  The probe has the shape of the real sample (32 issues) at a
+    quarter of the length."""
     import numpy as np
     import torch
     from oracle import awd_lstm_ref as R
     enc = R.make_encoder(1234, VOCAB, EMB, HID, N_LAYERS)
     cores = usable_cpus()
-    probe = np.stack(R.synthetic_ids(8, 16, seed=1))
+    probe = np.stack(R.synthetic_ids(CPU_SAMPLE_MIN, 128, seed=1))
     best = (0.0, 1)
     cands = sorted({c for c in (cores, cores // 2, 32, 16, 8) if 1 <= c <= cores}, reverse=True)
     for th in cands:
         torch.set_num_threads(th)
-        R.encode_padded(enc, probe, [16] * 8)
+        R.encode_padded(enc, probe[:8, :32], [32] * 8)   # warm the thread pool
         t0 = time.perf_counter()
-        R.encode_padded(enc, probe, [16] * 8)
-        rate = 8 * 16 / (time.perf_counter() - t0)
+        R.encode_padded(enc, probe, [128] * CPU_SAMPLE_MIN)
+        rate = CPU_SAMPLE_MIN * 128 / (time.perf_counter() - t0)
         if rate > best[0]:
             best = (rate, th)
     torch.set_num_threads(best[1])
     return enc, best[1], best[0], cores
 
 
+def cpu_sample_size(tok_rate, budget_s):
+    return int(max(CPU_SAMPLE_MIN, min(B, tok_rate * budget_s / T)))
+
+
 def cpu_oracle_rate(budget_s=20.0):
-    """issues/s of the CPU oracle on a bounded sample (about `budget_s` seconds) of the step's workload."""
+    """issues/s of the CPU oracle on a bounded sample (>= 32 issues, about `budget_s` seconds) of the step's workload."""
     import numpy as np
     from oracle import awd_lstm_ref as R
     enc, threads, tok_rate, cores = cpu_oracle_setup()
-    # per-step cost on the CPU is dominated by streaming the weights, so tokens/s grows with batch: size the
-    # sample from the probe conservatively and cap it at one full step
-    sb = int(max(1, min(B, tok_rate * budget_s / T)))
+    sb = cpu_sample_size(tok_rate, budget_s)
     ids = np.stack(R.synthetic_ids(sb, T, seed=2))
     t0 = time.perf_counter()
     out = R.encode_padded(enc, ids, [T] * sb)
@@ -172,8 +192,8 @@ def run_reference(args):
     import numpy as np
     from oracle import awd_lstm_ref as R
     enc, threads, tok_rate, cores = cpu_oracle_setup()
-    budget = 120.0 / max(1, args.steps + args.warmup)          # whole run within a few minutes
-    sb = int(max(1, min(B, tok_rate * budget / T)))
+    budget = 150.0 / max(1, args.steps + args.warmup)          # whole run within a few minutes
+    sb = cpu_sample_size(tok_rate, budget)
     ids = np.stack(R.synthetic_ids(sb, T, seed=3))
     for _ in range(args.warmup):
         R.encode_padded(enc, ids, [T] * sb)
@@ -199,10 +219,11 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=12)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=15)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -210,7 +231,7 @@ def main():
     import numpy as np
     import torch
     import torch.distributed as dist
-    from code_intelligence_b200 import IssueEncoder
+    from code_intelligence_b200 import IssueEncoder, bulk
     from oracle import awd_lstm_ref as R   # weights + synthetic ids generator + cpu_baseline leg only
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -227,18 +248,14 @@ def main():
     enc = IssueEncoder(N_LAYERS, EMB, HID, VOCAB, 1, local).load_weights(emb, layers)
     del ref
 
-    # distinct synthetic ids per step and per rank, resident in HBM for the `value` arm, pinned host for `e2e`
+    # distinct synthetic ids per step and per rank, resident in HBM for the `value` arm
     g = torch.Generator().manual_seed(1234 + rank)
     ids_all = torch.randint(0, VOCAB, (K + W, B, T), generator=g, dtype=torch.int64)
     ids_all[ids_all == 1] = 0
     ids_all[:, :, 0] = 2
     ids_dev = ids_all.to(dev)
-    ids_pin = ids_all.pin_memory()
-    len_dev = torch.full((B,), T, dtype=torch.int32, device=dev)
-    len_host = np.full(B, T, dtype=np.int32)
     out_dev = torch.empty((K * B, 3 * EMB), dtype=torch.float32, device=dev)
     gathered = torch.empty((world * K * B, 3 * EMB), dtype=torch.float32, device=dev) if world > 1 else None
-    out_pin = torch.empty((B, 3 * EMB), dtype=torch.float32).pin_memory()
     stream = torch.cuda.current_stream(dev)
 
     def barrier():
@@ -246,8 +263,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    # ---- launch plan: steps are submitted kPerLaunch at a time (3 x 256 rows per ie_encoder_encode call) ----------
-    kPerLaunch = max(1, enc.max_batch // B)   # 3; 5 with the experimental IE_ROT=1 kernel (csrc/lstm_rot.cu)
+    # ---- launch plan: steps are submitted kPerLaunch at a time (5 x 256 rows per ie_encoder_encode call) ----------
+    kPerLaunch = max(1, enc.max_batch // B)
     def plan(first, count, per_launch):
         # a remainder launch (count % per_launch steps) goes first, so that the LAST launch of a region -- whose
         # phase events feed the roofline -- is a full one
@@ -262,11 +279,7 @@ def main():
         return out
 
     ids_flat_dev = ids_dev.view((K + W) * B, T)
-    ids_flat_np = ids_pin.view((K + W) * B, T).numpy()
     len_dev2 = torch.full((kPerLaunch * B,), T, dtype=torch.int32, device=dev)
-    len_host2 = np.full(kPerLaunch * B, T, dtype=np.int32)
-    out_pin2 = torch.empty((kPerLaunch * B, 3 * EMB), dtype=torch.float32).pin_memory()
-    out_np2 = out_pin2.numpy()
 
     def run_device(first, count, per_launch):
         for (i, n) in plan(first, count, per_launch):
@@ -286,58 +299,93 @@ def main():
         e1.record(stream)
         barrier()
         ms = e0.elapsed_time(e1)
+        enc.check_errors()
         t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-        return float(t_ms.item()), enc.launch_count - l0, enc.last_phase_ms()
+        return float(t_ms.item()), enc.launch_count - l0, enc.last_phase_ms(), enc.last_phase_mhz()
 
     # ---- device-resident arm ------------------------------------------------------------------------
     sampler = ClockSampler(local)
-    ms_single, _, _ = device_arm(1)                  # one batch per launch (reported as `single_batch`)
+    ms_single, _, _, _ = device_arm(1)               # one batch per launch (reported as `single_batch`)
     if rank == 0:
         sampler.start()
-    ms_max, launches, phases = device_arm(kPerLaunch)  # three batches per launch: the bulk-encode mode
+    ms_max, launches, phases, phase_mhz = device_arm(kPerLaunch)   # five batches per launch: the bulk-encode mode
     value = world * B * K / (ms_max * 1e-3)
     single_value = world * B * K / (ms_single * 1e-3)
 
-    # ---- end-to-end arm: host buffers through the public API ----------------------------------------------
-    lib, h = enc._lib, enc._h
-    def run_host(first, count):
-        chk = 0.0
-        for (i, n) in plan(first, count, kPerLaunch):
-            rc = lib.ie_encoder_encode(h, ids_flat_np[i * B:(i + n) * B].ctypes.data, len_host2.ctypes.data, n * B, T,
-                                       out_np2.ctypes.data, 0, None)
-            assert rc == 0, lib.ie_last_error()
-            chk += float(out_np2[0, 0])
-        return chk
-    run_host(0, W)
+    # ---- end-to-end arm: HOST token-id lists through the public bulk API -----------------------------------
+    # every rank holds the same global list (the reference's per-repo list of numericalised issues), as the API expects
+    n_total = world * K * B
+    rng = np.random.default_rng(4321)
+    def make_docs(n, seed_rng):
+        a = seed_rng.integers(0, VOCAB, size=(n, T), dtype=np.int64)
+        a[a == 1] = 0
+        a[:, 0] = 2
+        return list(a)
+    docs_warm = make_docs(world * W * B, rng)
+    docs = make_docs(n_total, rng)
+    local_fn = lambda d: bulk.encode_sorted_batches_device(d, enc, min_batches_rule=False, to_host=False)
+    bulk.encode_bulk_distributed(docs_warm, local_fn, device=dev)
     barrier()
     t0 = time.perf_counter()
-    checksum = run_host(W, K)
-    torch.cuda.synchronize(dev)
-    e2e_s = time.perf_counter() - t0        # host-blocking API: wall time == device time + copies
+    res = bulk.encode_bulk_distributed(docs, local_fn, device=dev)      # -> np.ndarray (n_total, 2400) on the host
+    e2e_s = time.perf_counter() - t0
+    assert res.shape == (n_total, 3 * EMB) and np.isfinite(res[::97]).all()
     t_e2e = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * K / float(t_e2e.item())
+    e2e_value = n_total / float(t_e2e.item())
     clocks = sampler.stop() if rank == 0 else None
+
+    # ---- extras (rank 0 reports; all ranks take part where a collective is involved) ---------------------------
+    extra = {}
+    if not args.no_extra:
+        # var-len bulk encode, strong scaling: a FIXED list, sharded over the ranks, checked bit for bit against rank 0
+        # encoding the whole list alone
+        nv = 5120
+        rv = np.random.default_rng(99)
+        lens = rv.integers(64, T + 1, size=nv)
+        vdocs = []
+        for L in lens:
+            a = rv.integers(0, VOCAB, size=int(L), dtype=np.int64)
+            a[a == 1] = 0
+            a[0] = 2
+            vdocs.append(a)
+        bulk.encode_bulk_distributed(vdocs[:world * 256], local_fn, device=dev)
+        barrier()
+        t0 = time.perf_counter()
+        vres = bulk.encode_bulk_distributed(vdocs, local_fn, device=dev)
+        vs = time.perf_counter() - t0
+        t_v = torch.tensor([vs], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_v, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            alone = enc.encode_id_list(vdocs, min_batches_rule=False)
+            extra["bulk_varlen"] = {"issues": nv, "lengths": "uniform in [64, 512]", "valid_tokens": int(lens.sum()),
+                                    "value": nv / float(t_v.item()), "unit": "issues/s", "scaling": "strong",
+                                    "valid_tokens_per_s": float(lens.sum()) / float(t_v.item()),
+                                    "bit_equal_to_single_gpu": bool(np.array_equal(vres, alone))}
+        barrier()
+    if rank == 0 and not args.no_extra:
+        try:
+            extra.update(extras_rank0(enc, emb, layers, dev, R))
+        except Exception as e:   # extras never take the headline down
+            extra["error"] = repr(e)
 
     if rank == 0:
         peaks = measured_peaks()
         peak = (peaks or {}).get("bf16_tflops_sustained", 1400.0)
         peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback 1.4 PFLOP/s sustained"
-        # dominant kernel: the persistent recurrent kernel of the 2400-wide layers (one launch = all T steps of one
-        # layer for the batches riding the launch): avg launch duration from the CUDA events recorded around it inside
-        # ie_encoder_encode, last timed launch
         batches = kPerLaunch if K >= kPerLaunch else K   # batches riding the LAST timed launch (see plan())
         step_ms = phases["steps"][:N_LAYERS - 1]
         avg_launch_ms = sum(step_ms) / len(step_ms)
         flop_per_launch = STEP_FLOP_2400 * T * batches
         achieved = flop_per_launch / (avg_launch_ms * 1e-3) / 1e12
-        avg_launch_us = avg_launch_ms * 1e3
-        traffic = None
+        traffic, traffic_src = None, None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "lstm_seq_traffic.json")))["dram_bytes_per_launch"]
+            tj = json.load(open(os.path.join(ROOT, "profiles", "lstm_layer_traffic.json")))
+            traffic, traffic_src = tj["dram_bytes_per_launch"], tj.get("source")
         except Exception:
             pass
         line = {
@@ -346,23 +394,27 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": "configs[1]: 1M-issue bulk encode shape, fixed seq_len 512, batch 256 per step, "
                                    "R4 encoder (L=4,E=800,H=2400,V=60000) random-init seed 1234",
-                       "batch": B, "seq_len": T, "batches_per_launch": kPerLaunch, "parallelism": f"dp{world} (issues sharded, one all-gather of outputs)",
-                       "l2": "inputs larger than L2: each step streams ~6.5 GB of workspace (Gx 5 GB f32) and new ids",
-                       "operands": "bf16 weights/activations, f32 accumulate, f32 cell state and pooling"},
+                       "batch": B, "seq_len": T, "batches_per_launch": kPerLaunch,
+                       "parallelism": f"dp{world} (issues sharded, one all-gather of outputs)",
+                       "l2": "inputs larger than L2: each step streams ~3 GB of workspace (bf16 Gx, hidden-state rings) "
+                             "and new ids",
+                       "operands": "bf16 weights/activations/Gx, f32 accumulate, f32 cell state and pooling"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "issues/s", "h2d_bytes_per_step": B * T * 8 + B * 4,
-                    "d2h_bytes_per_step": B * 3 * EMB * 4 + 4},
+                    "d2h_bytes_per_step": world * B * 3 * EMB * 4,
+                    "api": "bulk.encode_bulk_distributed(host id lists) -> np.ndarray (N, 2400)"},
             "single_batch": {"value": single_value, "unit": "issues/s", "ms_per_step": ms_single / K,
                              "note": "same measurement with one batch of 256 per launch"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "tensor", "kernel": "%s (persistent recurrent kernel, 2400-wide layers, "
-                                   "%d batches in the last timed launch)" % (
-                                       "lstm_rot_kernel" if batches > 3 else "lstm_wide_kernel", batches),
+            "roofline": {"bound": "tensor", "kernel": "lstm_layer_kernel (persistent recurrent kernel, 2400-wide layers, "
+                                   "%d batches in the last timed launch)" % batches,
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "avg_launch_us": avg_launch_us,
-                         "flop_per_launch": flop_per_launch,
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                         "avg_launch_us": avg_launch_ms * 1e3, "flop_per_launch": flop_per_launch,
                          "whole_step_tflops": FLOP_PER_TOKEN * B * T / (ms_max / K * 1e-3) / 1e12,
-                         "phase_ms_last_step": phases},
+                         "whole_step_frac": FLOP_PER_TOKEN * B * T / (ms_max / K * 1e-3) / 1e12 / peak,
+                         "phase_ms_last_call": phases, "recurrent_kernel_sm_mhz": [round(x) for x in phase_mhz]},
+            "extra": extra,
         }
         if world == 1 and not args.no_cpu_baseline:
             rate, dt, threads, cores, sb = cpu_oracle_rate()
@@ -373,6 +425,78 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def extras_rank0(enc, emb, layers, dev, R):
+    """Secondary measurements on one GPU (device-resident inputs, CUDA events, after a warm-up call each)."""
+    import numpy as np
+    import torch
+    from code_intelligence_b200 import IssueEncoder, _lib
+    from code_intelligence_b200.mlp import MLPHead
+    out = {}
+    g = torch.Generator().manual_seed(7)
+
+    def time_encoder(e, rows, iters, flop_tok):
+        ids = torch.randint(2, VOCAB, (rows, T), generator=g, dtype=torch.int64).to(dev)
+        lens = torch.full((rows,), T, dtype=torch.int32, device=dev)
+        o = torch.empty((rows, 3 * EMB), dtype=torch.float32, device=dev)
+        e.encode_ids_device(ids, lens, o)
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            e.encode_ids_device(ids, lens, o)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        e.check_errors()
+        ms = e0.elapsed_time(e1) / iters
+        return {"value": rows / ms * 1e3, "unit": "issues/s", "rows_per_call": rows, "ms_per_256": ms * 256 / rows,
+                "tflops": flop_tok * rows * T / ms / 1e9}
+
+    # BASELINE configs[1] as written ("fp32"): split-bf16 products, f32 Gx, IEEE gates; parity in tests/test_gpu_parity.py
+    e32 = IssueEncoder(N_LAYERS, EMB, HID, VOCAB, 1, dev.index, _lib.IE_CFG_FP32).load_weights(emb, layers)
+    r = time_encoder(e32, e32.max_batch, 2, FLOP_PER_TOKEN)
+    r["note"] = ("IE_CFG_FP32: every product as three bf16 tensor-core passes (hi*hi + lo*hi + hi*lo), f32 accumulate; "
+                 "tflops counts the algorithmic (single-pass) FLOPs; rel-L2 vs the fp32 oracle <= 2e-5")
+    out["fp32_mode"] = r
+    e32.close()
+    # the north star's literal 3-layer shape
+    ref3 = R.make_encoder(1234, VOCAB, EMB, HID, 3)
+    emb3, layers3 = ref3.export_weights()
+    e3 = IssueEncoder(3, EMB, HID, VOCAB, 1, dev.index).load_weights(emb3, layers3)
+    out["n3"] = time_encoder(e3, e3.max_batch, 3, flop_per_token(3))
+    out["n3"]["note"] = "L=3 (800->2400->2400->800), same metric; 174.08 MFLOP/token"
+    e3.close()
+    # Label_Microservice head (configs[4]): (D_in -> 600 -> 600 -> 256), device-resident X, n = 2^20 rows
+    rng = np.random.default_rng(0)
+    for d_in in (1600, 2400):
+        dims = [d_in, 600, 600, 256]
+        coefs = [(rng.standard_normal((dims[i], dims[i + 1])) / np.sqrt(dims[i])).astype(np.float32) for i in range(3)]
+        ints = [(rng.standard_normal(dims[i + 1]) * 0.1).astype(np.float32) for i in range(3)]
+        head = MLPHead(coefs, ints, device=dev.index)
+        n = 1 << 20
+        X = torch.randn((n, d_in), generator=g).mul_(0.1).to(dev)
+        P = torch.empty((n, 256), dtype=torch.float32, device=dev)
+        head.predict_proba_device(X, P)
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            head.predict_proba_device(X, P)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / 3
+        flop = 2.0 * n * (d_in * 600 + 600 * 600 + 600 * 256)
+        byt = n * (d_in * 4 + 256 * 4)
+        peaks = measured_peaks() or {}
+        hbm = peaks.get("hbm_gbs", 6500.0)
+        out[f"mlp_{d_in}"] = {"rows_per_s": n / ms * 1e3, "labels_per_s": n * 256 / ms * 1e3, "ms": ms,
+                              "tflops": flop / ms / 1e9, "hbm_gbs": byt / ms / 1e6,
+                              "roofline": {"bound": "hbm", "achieved": byt / ms / 1e6, "peak": hbm, "unit": "GB/s",
+                                           "frac": byt / ms / 1e6 / hbm,
+                                           "note": "algorithmic bytes = f32 X in + f32 probabilities out"}}
+        head.close()
+    return out
 
 
 if __name__ == "__main__":

@@ -15,7 +15,8 @@ LIB_PATH = _PKG / "libissue_emb_b200.so"
 
 IE_OK, IE_ERR_INVALID, IE_ERR_CUDA, IE_ERR_OOM, IE_ERR_STATE, IE_ERR_TOKEN = 0, -1, -2, -3, -4, -5
 IE_FLAG_DEVICE_PTRS = 1
-IE_MAX_BATCH = 768
+IE_MAX_BATCH = 2048          # upper bound; a handle's own limit is ie_encoder_max_batch() (1280 by default)
+IE_CFG_ACCURATE_GATES, IE_CFG_FP32, IE_CFG_F32_GX = 1, 2, 4
 
 
 class ie_config(C.Structure):
@@ -37,9 +38,10 @@ PROTOTYPES = {
                                           C.c_void_p]),
     "ie_encoder_launch_count": (C.c_int64, [C.c_void_p]),
     "ie_encoder_max_batch": (C.c_int32, [C.c_void_p]),
+    "ie_encoder_check_errors": (C.c_int, [C.c_void_p]),
     "ie_encoder_last_phase_ms": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32]),
+    "ie_encoder_last_phase_mhz": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32]),
     "ie_debug_seq_trace": (C.c_int64, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64]),
-    "ie_debug_umma_rate": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "ie_mlp_create": (C.c_int, [C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_void_p)]),
     "ie_mlp_load_layer": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "ie_mlp_predict_proba": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),

@@ -59,6 +59,92 @@ def encode_sorted_batches(docs: List[np.ndarray], encode_padded: Callable, pad_i
     return pooled[len_mask_reversed, :]
 
 
+def encode_sorted_batches_device(docs: List[np.ndarray], enc, bs: int = 100, min_batches_rule: bool = True,
+                                 coalesce: bool = True, to_host: bool = True):
+    """The same bulk loop as ``encode_sorted_batches`` driven as a pipeline on the GPU (``enc``: an ``IssueEncoder``):
+    the padded batch k+1 is packed into pinned host memory and copied to the device on a side stream while the kernels
+    of batch k run (two staging slots, events instead of host synchronisation), the pooled rows of every batch land in
+    one device tensor, and the un-sort (argsort(argsort), py/code_intelligence/inference.py:226) is one device gather.
+    ``IE_ERR_OOM`` still surfaces as ``RuntimeError`` at the call that needed the memory (workspace is allocated before
+    anything is launched), so the reference's halving loop (:214-223) keeps its meaning.
+    Returns np.ndarray (N, D) float32 in input order, or the device tensor with ``to_host=False``."""
+    import torch
+    n = len(docs)
+    D = enc.out_dim
+    dev = torch.device("cuda", enc.device)
+    if n == 0:
+        return np.empty((0, D), dtype=np.float32) if to_host else torch.empty((0, D), dtype=torch.float32, device=dev)
+    max_bs = enc.max_batch
+    if min_batches_rule:
+        bs = min(bs, (n // 20) + 1)
+    bs = max(1, min(bs, max_bs))
+    if coalesce:
+        bs = max_bs
+    length_arr = np.array([len(d) for d in docs])
+    if (length_arr < 1).any():
+        raise ValueError("empty token sequence")
+    len_mask = length_arr.argsort(kind="stable")
+    ordered_lengths = length_arr[len_mask]
+    with torch.cuda.device(dev):
+        out = torch.empty((n, D), dtype=torch.float32, device=dev)      # sorted order
+        cur = torch.cuda.current_stream(dev)
+        side = torch.cuda.Stream(dev)
+
+        class Slot:
+            def __init__(self):
+                self.ids_pin = self.len_pin = self.ids_dev = self.len_dev = None
+                self.h2d_done, self.compute_done = torch.cuda.Event(), torch.cuda.Event()
+                self.used = False
+
+            def reserve(self, tokens, rows):
+                if self.ids_pin is None or self.ids_pin.numel() < tokens:
+                    self.ids_pin = torch.empty(tokens, dtype=torch.int64).pin_memory()
+                    self.ids_dev = torch.empty(tokens, dtype=torch.int64, device=dev)
+                if self.len_pin is None or self.len_pin.numel() < rows:
+                    self.len_pin = torch.empty(rows, dtype=torch.int32).pin_memory()
+                    self.len_dev = torch.empty(rows, dtype=torch.int32, device=dev)
+
+        slots = [Slot(), Slot()]
+        i, k = 0, 0
+        while i < n:
+            nb = min(bs, n - i)
+            idx = len_mask[i:i + nb]
+            T = int(ordered_lengths[i + nb - 1])
+            st = slots[k & 1]
+            if st.used:
+                st.compute_done.synchronize()       # the slot's device buffers (and so its staging) are free again
+            st.reserve(nb * T, nb)
+            bp = st.ids_pin[:nb * T].view(nb, T).numpy()
+            lens = ordered_lengths[i:i + nb]
+            if int(lens[0]) == T:                    # fixed-length batch: one vectorised copy
+                bp[:] = np.stack([docs[j] for j in idx])
+            else:
+                bp.fill(enc.pad_idx)
+                for r, j in enumerate(idx):
+                    bp[r, :length_arr[j]] = docs[j]
+            st.len_pin[:nb].numpy()[:] = lens
+            with torch.cuda.stream(side):
+                st.ids_dev[:nb * T].copy_(st.ids_pin[:nb * T], non_blocking=True)
+                st.len_dev[:nb].copy_(st.len_pin[:nb], non_blocking=True)
+                st.h2d_done.record(side)
+            cur.wait_event(st.h2d_done)
+            try:
+                enc.encode_ids_device(st.ids_dev[:nb * T].view(nb, T), st.len_dev[:nb], out[i:i + nb], cur)
+            except RuntimeError as e:
+                if bs == 1:
+                    raise Exception(e)
+                bs = max(1, nb // 2)                 # halve what was actually attempted and retry the same position
+                continue
+            st.compute_done.record(cur)
+            st.used = True
+            i += nb
+            k += 1
+        enc.check_errors()                           # token ids out of range etc. (device-pointer calls are asynchronous)
+        inv = torch.as_tensor(len_mask.argsort(), device=dev)
+        res = out.index_select(0, inv)
+    return res.cpu().numpy() if to_host else res
+
+
 def shard_plan(lengths: np.ndarray, world: int):
     """-> (order, shards): order = stable argsort by length; shards[r] = input indices of rank r (sorted order)."""
     order = np.asarray(lengths).argsort(kind="stable")
@@ -84,10 +170,12 @@ def gather_rows(local, n_total: int, world: int, rank: int, group=None):
 
 
 def encode_bulk_distributed(docs: List[np.ndarray], encode_local: Callable[[List[np.ndarray]], "np.ndarray"],
-                            device: Optional[str] = None, group=None) -> np.ndarray:
+                            device: Optional[str] = None, group=None, to_host: bool = True):
     """Every rank passes the same ``docs`` (the reference's per-repo list) and gets the full (N, D) float32 array in
-    input order.  ``encode_local(list_of_id_arrays) -> (n, D)`` is the per-rank encoder, e.g.
-    ``IssueEncoder.encode_id_list`` with ``min_batches_rule=False``."""
+    input order.  ``encode_local(list_of_id_arrays) -> (n, D)`` is the per-rank encoder; it may return a numpy array
+    (CPU / gloo tests) or a torch tensor that already lives on the GPU -- e.g.
+    ``lambda d: bulk.encode_sorted_batches_device(d, enc, min_batches_rule=False, to_host=False)`` -- in which case
+    nothing bounces through the host: the all-gather (NCCL over NVLink) and the inverse permutation run on the device."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -98,17 +186,21 @@ def encode_bulk_distributed(docs: List[np.ndarray], encode_local: Callable[[List
     mine = [docs[i] for i in shards[rank]]
     local = encode_local(mine) if len(mine) else None
     if local is None:
-        local = np.zeros((0, 1), dtype=np.float32)
-    lt = torch.as_tensor(np.ascontiguousarray(local, dtype=np.float32))
+        lt = torch.zeros((0, 0), dtype=torch.float32)
+    elif isinstance(local, torch.Tensor):
+        lt = local.to(torch.float32)
+    else:
+        lt = torch.as_tensor(np.ascontiguousarray(local, dtype=np.float32))
+    if device is not None and str(lt.device) != str(device):
+        lt = lt.to(device)
     # every rank must agree on D even when its shard is empty
-    d_t = torch.tensor([lt.shape[1] if lt.shape[0] else 0], dtype=torch.int64)
-    if device is not None:
-        lt, d_t = lt.to(device), d_t.to(device)
+    d_t = torch.tensor([lt.shape[1] if lt.shape[0] else 0], dtype=torch.int64, device=lt.device)
     if world > 1:
         dist.all_reduce(d_t, op=dist.ReduceOp.MAX, group=group)
     D = int(d_t.item())
     if lt.shape[0] == 0:
         lt = torch.zeros((0, D), dtype=torch.float32, device=lt.device)
-    sorted_rows = gather_rows(lt, n, world, rank, group)
-    inv = order.argsort()
-    return sorted_rows.cpu().numpy()[inv]
+    sorted_rows = gather_rows(lt.contiguous(), n, world, rank, group)
+    inv = torch.as_tensor(order.argsort(), device=sorted_rows.device)
+    res = sorted_rows.index_select(0, inv)
+    return res.cpu().numpy() if to_host else res

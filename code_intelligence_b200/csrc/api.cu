@@ -79,12 +79,11 @@ struct DevBuf {
 
 struct Layer {
   int in = 0, out = 0;      // logical dims
-  int u = 0, n_cta = 0;     // hidden units per CTA, CTAs per step
+  int u = 32, n_cta = 0;    // hidden units per weight slice (CTA), slices (even: CTA pairs own two)
   int out_pad = 0;          // n_cta * u
   int kin_pad = 0;          // padded K of the input projection
   int kh_pad = 0;           // padded K of the recurrent projection
   int bn = 0;               // GEMM N tile for the input projection
-  int cluster = 1;          // CTAs per cluster in the recurrent step (h tiles shared by TMA multicast)
   DevBuf w_ih, w_hh, bias;  // sliced layouts
   bool loaded = false;
 };
@@ -95,38 +94,45 @@ struct ie_encoder {
   ie_config cfg{};
   int num_sms = 148;
   int e_pad = 0;  // emb_sz rounded up to 64
-  std::vector<Layer> layers;   // plan A: u ~ out/148 units per CTA (N = 160 pair tiles at H = 2400): B <= 512
-  std::vector<Layer> layersB;  // plan B: u = 32 (N = 256 pair tiles): three batches per launch (512 < B <= 768)
-  int use_wide = 1, wide_checked = 0;
-  // experimental (IE_ROT=1): rotating item schedule (lstm_rot.cu), up to kRotMaxBatches batches per launch on plan B;
-  // IE_ROT=2 also routes 256..768 rows through it (for testing).  max_batch is what ie_encoder_encode accepts.
-  int use_rot = 0, rot_checked = 0, rot_variant = 0;  // rot_variant: IE_ROT_VARIANT (LstmWideArgs::variant)
-  int max_batch = IE_MAX_BATCH;
-  // experimental (IE_EMB_PROJ=1): layer 0's input projection W_ih0 . Emb[id] + b is a function of the token id alone,
-  // so it is tabulated once per weight set (proj: [vocab_pad, 4*out_pad] f32, plan-B column order, computed by the same
-  // GEMM from the same bf16 operands => the same bits) and the wide / rotating kernels read row tok[t, b] of it:
-  // no embedding gather, no layer-0 GEMM, no Gx write for that layer.
-  int use_proj = 0;
-  // experimental (IE_POOL_RAW=1): in wide / rotating calls the last layer writes its f32 h_t to `raw` and a separate
-  // kernel pools it (same sequential sums => same bits); the recurrent epilogue carries no pooling accumulators
-  int use_pool_raw = 0;
+  // one weight layout: slices of u = 32 hidden units, rows [slice][unit][gate]; a CTA pair owns two slices = one
+  // N = 256 accumulator tile (lstm_layer.cu), the fallback kernel one slice per CTA (lstm.cu)
+  std::vector<Layer> layers;
+  int segs = 1;            // 1: bf16 operands; 3: split-bf16 ("fp32-accurate", IE_CFG_FP32)
+  int gate_mode = 2;       // lstm_common.cuh: 2 tanh.approx, 1 ex2+rcp, 0 IEEE
+  int gx_bf16 = 1;         // input projections (Gx, per-token table) stored as bf16 (f32 in the fp32-accurate mode)
+  int use_persistent = 1;  // cooperative persistent kernel; 0 (IE_SEQ=0 or not co-resident): per-timestep fallback
+  int persist_checked = 0;
+  int cooperative = 1;     // launch attribute (IE_COOP=0: plain launch, co-residency by the occupancy check only)
+  int batches = 5;         // batches of 256 rows one launch takes (IE_BATCHES, <= kMaxBatches)
+  int max_batch = 1280;
+  // layer 0's input projection W_ih0 . Emb[id] + b depends on the token id alone: tabulated once per weight set
+  // (proj: [vocab_pad, 4*out_pad], computed by the same GEMM from the same operands => the same bits as gather + GEMM)
+  // and the recurrent kernel reads row tok[t, b] of it: no embedding gather, no layer-0 GEMM, no Gx write for layer 0
+  int use_proj = 1;
   bool proj_built = false;
   DevBuf proj, tok;
-  DevBuf emb;  // bf16 [vocab, e_pad]
+  DevBuf emb;  // bf16 [vocab_pad, e_pad] (split mode: [hi | lo])
   bool emb_loaded = false;
+  long long spin_limit = 0;  // SM cycles a device-side wait may take (0: default ~2 s); IE_SPIN_LIMIT_MS
+  int fault = 0;             // IE_DEBUG_FAULT: exercise the abort protocol
+  long long chunk_t = 0;     // IE_CHUNK_T: force the time-chunk length (testing)
   // workspace
-  DevBuf ids, lengths, x0, y[2], gx, c, pool_sum, pool_max, pool_last, out, raw, err, step_done;
+  DevBuf ids, len_in, lengths, x0, y[2], hcarry, gx, c, pool_sum, pool_max, pool_last, out, raw, err, step_done, diag;
   DevBuf trace;           // debug timeline of one layer of the persistent kernel (ie_debug_seq_trace)
   int trace_layer = -1;
   int trace_T = 0, trace_ctas = 0;
-  int fast_math = 1;      // tanh.approx gates in the persistent kernel (ie_config.flags & IE_CFG_ACCURATE_GATES: off)
-  int use_seq = 1;        // persistent per-layer kernel (lstm_seq.cu) when B_pad == 256 and the grid is co-resident
-  int seq_checked = 0;    // co-residency verified for every layer
   long long y_ld = 0;
+  long long ws_tokens = 0;  // largest b_pad*T the workspace was grown for
+  int small_calls = 0;      // consecutive calls far below ws_tokens (workspace is released after a few)
   cudaStream_t own_stream = nullptr;
+  cudaStream_t last_stream = nullptr;
+  cudaEvent_t done_ev = nullptr;  // end of the last call: a call on another stream waits for it (shared workspace)
+  bool has_done = false;
   int64_t launches = 0;
-  // phase boundary events of the last encode call: start, gather, (gemm_l, steps_l) x L, finalize
+  // phase boundary events of the last encode call and what ended at each (0 start, 1 gather, 2+2l gemm_l, 3+2l steps_l,
+  // 2+2L finalize)
   std::vector<cudaEvent_t> ev;
+  std::vector<int> ev_tag;
   int ev_used = 0;
   int last_T = 0, last_b_pad = 0;
   std::mutex mu;
@@ -150,43 +156,31 @@ struct ie_mlp {
 
 namespace {
 
-constexpr int kStepStride = ie::kRotMaxBatches;  // step counters per (layer, timestep): one per batch of the launch
+constexpr int kErrWords = 4;  // err[0] token id out of range, err[1] device-side wait timed out (abort protocol),
+                              // err[2] a length had to be clamped (device-pointer mode)
 
-int plan_layers(ie_encoder* h, std::vector<Layer>& layers, int u_fixed) {
+int plan_layers(ie_encoder* h) {
   const ie_config& c = h->cfg;
   h->e_pad = static_cast<int>(round_up(c.emb_sz, 64));
-  layers.resize(c.n_layers);
+  h->layers.resize(c.n_layers);
   int prev_pad = h->e_pad;
   for (int l = 0; l < c.n_layers; ++l) {
-    Layer& L = layers[l];
+    Layer& L = h->layers[l];
     L.in = (l == 0) ? c.emb_sz : c.n_hid;
     L.out = (l == c.n_layers - 1) ? c.emb_sz : c.n_hid;
-    // u hidden units per CTA: multiple of 4, as many CTAs as fit on the SMs (one wave)
-    L.u = u_fixed > 0 ? u_fixed : 4 * static_cast<int>((L.out + 4ll * h->num_sms - 1) / (4ll * h->num_sms));
-    if (L.u > 32) return fail(IE_ERR_INVALID, "hidden size %d too large for %d SMs", L.out, h->num_sms);
+    L.u = 32;
     L.n_cta = (L.out + L.u - 1) / L.u;
-    if (u_fixed > 0 && (L.n_cta & 1)) ++L.n_cta;  // CTA pairs: the last pair's second slice is pure padding
+    if (L.n_cta & 1) ++L.n_cta;  // CTA pairs: the last pair's second slice is pure padding
     L.out_pad = L.n_cta * L.u;
     L.kin_pad = prev_pad;
-    L.kh_pad = static_cast<int>(round_up(L.out_pad, 64));
+    L.kh_pad = L.out_pad;        // multiple of 64
     prev_pad = L.kh_pad;
-    // cluster size for the h-tile multicast in the per-step fallback kernel: largest of 8/4/2/1 <= want dividing n_cta.
-    // Measured (profiles/README.md): multicast changes nothing there, so the default is no clusters.
-    int want = 1;
-    if (const char* e = getenv("IE_STEP_CLUSTER")) want = atoi(e);
-    L.cluster = 1;
-    for (int cs = 8; cs >= 1; cs >>= 1)
-      if (cs <= want && L.n_cta % cs == 0) { L.cluster = cs; break; }
-    // largest multiple of 16 <= 256 dividing 4*out_pad
-    const int n = 4 * L.out_pad;
-    L.bn = 16;
-    for (int b = 256; b >= 16; b -= 16)
-      if (n % b == 0) { L.bn = b; break; }
+    L.bn = 256;                  // 4*out_pad is a multiple of 256
   }
   return IE_OK;
 }
 
-// torch gate-major rows [4*out] -> sliced rows [cta][unit][gate]; -1 marks zero padding rows
+// torch gate-major rows [4*out] -> sliced rows [slice][unit][gate]; -1 marks zero padding rows
 std::vector<int> slice_perm(const Layer& L) {
   std::vector<int> perm(4 * static_cast<size_t>(L.out_pad));
   for (int j = 0; j < L.n_cta; ++j)
@@ -198,89 +192,136 @@ std::vector<int> slice_perm(const Layer& L) {
   return perm;
 }
 
-int upload_sliced(const float* host, int rows_src, int cols, const std::vector<int>& perm, int ld_dst, DevBuf& dst,
+// host f32 [rows_src, cols] -> device bf16 [perm.size(), ld] (split mode: [hi(k_pad) | lo(k_pad)], ld = 2*k_pad)
+int upload_sliced(const float* host, int rows_src, int cols, const std::vector<int>& perm, int k_pad, int segs, DevBuf& dst,
                   cudaStream_t s) {
   DevBuf tmp, dperm;
+  const int ld_dst = segs > 1 ? 2 * k_pad : k_pad;
   CK(tmp.reserve(static_cast<size_t>(rows_src) * cols * sizeof(float)));
   CK(dperm.reserve(perm.size() * sizeof(int)));
   CK(cudaMemcpyAsync(tmp.p, host, static_cast<size_t>(rows_src) * cols * sizeof(float), cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(dperm.p, perm.data(), perm.size() * sizeof(int), cudaMemcpyHostToDevice, s));
   CK(dst.reserve(perm.size() * static_cast<size_t>(ld_dst) * sizeof(__nv_bfloat16)));
   CK(ie::launch_convert_rows(tmp.as<float>(), cols, cols, dperm.as<int>(), static_cast<int>(perm.size()),
-                             dst.as<__nv_bfloat16>(), ld_dst, s));
+                             dst.as<__nv_bfloat16>(), ld_dst, segs > 1 ? k_pad : 0, s));
   CK(cudaStreamSynchronize(s));
   tmp.release();
   dperm.release();
   return IE_OK;
 }
 
-int ensure_workspace(ie_encoder* h, int b_pad, int T, bool want_raw) {
+long long max_out_pad(const ie_encoder* h) {
+  long long m = 0;
+  for (const Layer& L : h->layers) m = std::max<long long>(m, L.out_pad);
+  return m;
+}
+
+void release_workspace(ie_encoder* h) {
+  DevBuf* bufs[] = {&h->ids, &h->x0, &h->y[0], &h->y[1], &h->gx, &h->raw, &h->step_done, &h->tok};
+  for (DevBuf* b : bufs) b->release();
+  h->ws_tokens = 0;
+  h->small_calls = 0;
+}
+
+// The time dimension is processed in chunks of chunk_T steps (time-major: every layer runs a chunk before the next
+// chunk starts; c and h are carried per layer), so everything but the token ids is bounded by chunk_T * b_pad rows.
+int ensure_workspace(ie_encoder* h, int b_pad, int T, int chunk_T, bool want_raw, bool need_x0, bool need_tok) {
   const ie_config& c = h->cfg;
-  long long max_out_pad = 0, max_kh = 0;
-  for (const std::vector<Layer>* plan : {&h->layers, &h->layersB})
-    for (const Layer& L : *plan) {
-      max_out_pad = std::max<long long>(max_out_pad, L.out_pad);
-      max_kh = std::max<long long>(max_kh, L.kh_pad);
-    }
+  const long long mop = max_out_pad(h);
   const long long rows = static_cast<long long>(T) * b_pad;
+  const long long crow = static_cast<long long>(chunk_T) * b_pad;
+  const int ring_mul = h->segs > 1 ? 2 : 1;
   CK(h->ids.reserve(static_cast<size_t>(h->max_batch) * T * sizeof(int64_t)));
+  CK(h->len_in.reserve(h->max_batch * sizeof(int)));
   CK(h->lengths.reserve(h->max_batch * sizeof(int)));
-  CK(h->err.reserve(sizeof(int), true));
-  CK(h->x0.reserve(static_cast<size_t>(rows) * h->e_pad * sizeof(__nv_bfloat16)));
-  // hidden-state rings: (T+1) slots of b_pad rows; slot 0 and the K padding columns must be zero
-  h->y_ld = max_kh;
-  const size_t ybytes = static_cast<size_t>(rows + b_pad) * max_kh * sizeof(__nv_bfloat16);
-  for (int i = 0; i < 2; ++i) CK(h->y[i].reserve(ybytes, /*zero=*/true));
-  CK(h->gx.reserve(static_cast<size_t>(rows) * 4 * max_out_pad * sizeof(float)));
-  CK(h->c.reserve(static_cast<size_t>(h->max_batch) * max_out_pad * sizeof(float)));
-  const size_t pb = static_cast<size_t>(h->max_batch) * max_out_pad * sizeof(float);
+  CK(h->err.reserve(kErrWords * sizeof(int), true));
+  CK(h->diag.reserve(static_cast<size_t>(c.n_layers) * 4 * sizeof(long long), true));
+  if (need_x0) CK(h->x0.reserve(static_cast<size_t>(crow) * ring_mul * h->e_pad * sizeof(__nv_bfloat16)));
+  // hidden-state rings of one chunk: (chunk_T + 1) slots of b_pad rows; slot 0 = the layer's h before the chunk (carry).
+  // Every column a tensor map can reach is written before it is read (padded units produce exact zeros).
+  h->y_ld = ring_mul * mop;
+  const size_t ybytes = static_cast<size_t>(crow + b_pad) * h->y_ld * sizeof(__nv_bfloat16);
+  for (int i = 0; i < 2; ++i) CK(h->y[i].reserve(ybytes));
+  CK(h->hcarry.reserve(static_cast<size_t>(c.n_layers) * h->max_batch * h->y_ld * sizeof(__nv_bfloat16)));
+  CK(h->gx.reserve(static_cast<size_t>(crow) * 4 * mop * (h->gx_bf16 ? 2 : 4)));
+  CK(h->c.reserve(static_cast<size_t>(c.n_layers) * h->max_batch * mop * sizeof(float)));
+  const size_t pb = static_cast<size_t>(h->max_batch) * mop * sizeof(float);
   CK(h->pool_sum.reserve(pb));
   CK(h->pool_max.reserve(pb));
   CK(h->pool_last.reserve(pb));
   CK(h->out.reserve(static_cast<size_t>(h->max_batch) * 3 * c.emb_sz * sizeof(float)));
-  if (want_raw) CK(h->raw.reserve(static_cast<size_t>(b_pad) * T * max_out_pad * sizeof(float)));
-  CK(h->step_done.reserve(static_cast<size_t>(c.n_layers) * T * kStepStride * sizeof(unsigned)));
-  if (h->use_proj) CK(h->tok.reserve(static_cast<size_t>(rows) * sizeof(int)));
+  if (want_raw) CK(h->raw.reserve(static_cast<size_t>(b_pad) * T * mop * sizeof(float)));
+  CK(h->step_done.reserve(static_cast<size_t>(chunk_T) * ie::kMaxBatches * sizeof(unsigned)));
+  if (need_tok) CK(h->tok.reserve(static_cast<size_t>(rows) * sizeof(int)));
+  h->ws_tokens = std::max(h->ws_tokens, crow);
   return IE_OK;
 }
 
-int mark(ie_encoder* h, cudaStream_t s) {
+int mark(ie_encoder* h, int tag, cudaStream_t s) {
   if (h->ev_used >= static_cast<int>(h->ev.size())) {
     cudaEvent_t e;
     CK(cudaEventCreate(&e));
     h->ev.push_back(e);
+    h->ev_tag.push_back(0);
   }
+  h->ev_tag[h->ev_used] = tag;
   CK(cudaEventRecord(h->ev[h->ev_used++], s));
   return IE_OK;
 }
 
-// IE_EMB_PROJ: tabulate layer 0's input projection for every token id (once per weight set)
-int build_proj_table(ie_encoder* h, cudaStream_t s) {
-  const Layer& L = h->layersB[0];
+bool proj_usable(const ie_encoder* h) {
+  if (!h->use_proj) return false;
+  const Layer& L = h->layers[0];
   const long long v_pad = round_up(h->cfg.vocab_sz, 256);
-  if (h->emb.cap < static_cast<size_t>(v_pad) * h->e_pad * sizeof(__nv_bfloat16))
-    return fail(IE_ERR_STATE, "embedding was loaded without row padding (IE_EMB_PROJ must be set before loading)");
-  CK(h->proj.reserve(static_cast<size_t>(v_pad) * 4 * L.out_pad * sizeof(float)));
-  ie::GemmArgs g{};
-  g.a = h->emb.as<__nv_bfloat16>();
-  g.lda = h->e_pad;
+  const long long bytes = v_pad * 4ll * L.out_pad * (h->gx_bf16 ? 2 : 4);
+  return bytes <= (6ll << 30);  // huge vocabularies fall back to gather + GEMM
+}
+
+void fill_gemm(const ie_encoder* h, const Layer& L, ie::GemmArgs& g) {
   g.b = L.w_ih.as<__nv_bfloat16>();
-  g.ldb = L.kin_pad;
-  g.d = h->proj.p;
+  g.ldb = static_cast<long long>(h->segs > 1 ? 2 : 1) * L.kin_pad;
   g.ldd = 4ll * L.out_pad;
   g.bias = L.bias.as<float>();
-  g.m_pad = static_cast<int>(v_pad);
   g.n_pad = 4 * L.out_pad;
   g.k_pad = L.kin_pad;
-  g.m_store = static_cast<int>(v_pad);
   g.n_store = 4 * L.out_pad;
   g.bn = L.bn;
   g.act = 0;
-  g.out_bf16 = 0;
+  g.out_bf16 = h->gx_bf16;
   g.num_sms = h->num_sms;
+  g.segs = h->segs;
+  g.abort_flag = h->err.as<unsigned>() + 1;
+  g.spin_limit = h->spin_limit;
+}
+
+// tabulate layer 0's input projection for every token id (once per weight set)
+int build_proj_table(ie_encoder* h, cudaStream_t s) {
+  const Layer& L = h->layers[0];
+  const long long v_pad = round_up(h->cfg.vocab_sz, 256);
+  CK(h->proj.reserve(static_cast<size_t>(v_pad) * 4 * L.out_pad * (h->gx_bf16 ? 2 : 4)));
+  ie::GemmArgs g{};
+  fill_gemm(h, L, g);
+  g.a = h->emb.as<__nv_bfloat16>();
+  g.lda = static_cast<long long>(h->segs > 1 ? 2 : 1) * h->e_pad;
+  g.d = h->proj.p;
+  g.m_pad = static_cast<int>(v_pad);
+  g.m_store = static_cast<int>(v_pad);
   CK(ie::launch_gemm_bf16(g, s));
   h->launches++;
   h->proj_built = true;
+  return IE_OK;
+}
+
+int check_persistent(ie_encoder* h, cudaStream_t s) {
+  if (h->persist_checked) return IE_OK;
+  for (const Layer& L : h->layers) {
+    ie::LstmLayerArgs q{};
+    q.T = 1; q.ng = 1; q.u = L.u; q.n_cta = L.n_cta; q.out_pad = L.out_pad; q.kh_pad = L.kh_pad; q.segs = 1;
+    q.num_sms = h->num_sms; q.check_only = 1;
+    if (ie::launch_lstm_layer(q, s) != cudaSuccess) h->use_persistent = 0;
+  }
+  cudaGetLastError();
+  h->persist_checked = 1;
   return IE_OK;
 }
 
@@ -291,55 +332,43 @@ int run_encoder(ie_encoder* h, const int64_t* ids, const int32_t* lengths, int B
   if (!h->emb_loaded) return fail(IE_ERR_STATE, "embedding not loaded");
   for (const Layer& L : h->layers)
     if (!L.loaded) return fail(IE_ERR_STATE, "LSTM layer weights not loaded");
-  for (const Layer& L : h->layersB)
-    if (!L.loaded) return fail(IE_ERR_STATE, "LSTM layer weights not loaded");
   if (B < 1 || B > h->max_batch) return fail(IE_ERR_INVALID, "B=%d outside [1,%d]", B, h->max_batch);
   if (T < 1) return fail(IE_ERR_INVALID, "T=%d must be >= 1", T);
   if (ids == nullptr || (out == nullptr && raw_out == nullptr)) return fail(IE_ERR_INVALID, "null pointer");
   const bool dev = (flags & IE_FLAG_DEVICE_PTRS) != 0;
   const bool pooled = out != nullptr;
-  const int b_pad = B <= 128 ? 128 : static_cast<int>(round_up(B, 256));
-  if (h->use_rot && !h->rot_checked) {  // every CTA pair of the rotating-schedule kernel must be co-resident
-    CK(cudaSetDevice(c.device));
-    for (const Layer& L : h->layersB) {
-      ie::LstmWideArgs q{};
-      q.T = 1; q.ng = 1; q.u = L.u; q.n_cta = L.n_cta; q.out_pad = L.out_pad; q.kh_pad = L.kh_pad;
-      q.num_sms = h->num_sms; q.check_only = 1; q.variant = h->rot_variant;
-      if (ie::launch_lstm_rot(q, s) != cudaSuccess) h->use_rot = 0;
-    }
-    cudaGetLastError();
-    h->rot_checked = 1;
-  }
-  const bool rot = h->use_rot && b_pad >= 256 && (b_pad > 768 || h->use_rot >= 2);
-  const bool wide = (b_pad == 768) && !rot;
-  if (b_pad > 768 && !rot) return fail(IE_ERR_STATE, "B > 768 needs the rotating-schedule kernel (caller splits the batch)");
-  std::vector<Layer>& LS = (wide || rot) ? h->layersB : h->layers;
-  // workspace cap (tokens per call); IE_MAX_TOKENS lowers it, e.g. to exercise the caller's batch-halving loop
-  long long cap = 1ll << 21;
-  if (const char* e = getenv("IE_MAX_TOKENS")) cap = std::max(128ll, atoll(e));
+  const int ng = (B + 255) / 256;
+  const int b_pad = 256 * ng;
+  // IE_MAX_TOKENS: artificial cap on B_pad*T (exercises the callers' OOM batch-halving loop); real limits come from
+  // cudaMalloc (-> IE_ERR_OOM) -- only the token ids grow with T, everything else is bounded by the time chunk
+  long long cap = 1ll << 27;
+  if (const char* e = getenv("IE_MAX_TOKENS")) cap = std::max(256ll, atoll(e));
   if (static_cast<long long>(b_pad) * T > cap)
     return fail(IE_ERR_OOM, "B_pad*T = %lld tokens exceeds the workspace cap %lld; use a smaller batch",
                 static_cast<long long>(b_pad) * T, cap);
   CK(cudaSetDevice(c.device));
-  const bool pool_raw = h->use_pool_raw && pooled && raw_out == nullptr && (wide || rot);
-  int rc = ensure_workspace(h, b_pad, T, raw_out != nullptr || pool_raw);
+  long long chunk_T = std::max<long long>(1, (1ll << 20) / b_pad);  // <= 2^20 (timestep, row) pairs of Gx at once
+  if (h->chunk_t > 0) chunk_T = h->chunk_t;
+  chunk_T = std::min<long long>(chunk_T, T);
+  const bool proj = proj_usable(h);
+  int rc = ensure_workspace(h, b_pad, T, static_cast<int>(chunk_T), raw_out != nullptr, !proj, proj);
   if (rc != IE_OK) return rc;
+  if (h->done_ev == nullptr) CK(cudaEventCreateWithFlags(&h->done_ev, cudaEventDisableTiming));
+  // one workspace per handle: a call on another stream first waits for the previous call
+  if (h->has_done && h->last_stream != s) CK(cudaStreamWaitEvent(s, h->done_ev, 0));
 
-  // lengths: validate on the host when we can; padded rows get length 1
-  std::vector<int> len_host(h->max_batch, 1);
+  CK(cudaMemsetAsync(h->err.p, 0, kErrWords * sizeof(int), s));
   if (pooled) {
     if (lengths == nullptr) return fail(IE_ERR_INVALID, "lengths is null");
+    const int* len_src = lengths;
     if (!dev) {
-      for (int b = 0; b < B; ++b) {
+      for (int b = 0; b < B; ++b)
         if (lengths[b] < 1 || lengths[b] > T)
           return fail(IE_ERR_INVALID, "lengths[%d]=%d outside [1,%d]", b, lengths[b], T);
-        len_host[b] = lengths[b];
-      }
-      CK(cudaMemcpyAsync(h->lengths.p, len_host.data(), h->max_batch * sizeof(int), cudaMemcpyHostToDevice, s));
-    } else {
-      CK(cudaMemcpyAsync(h->lengths.p, len_host.data(), h->max_batch * sizeof(int), cudaMemcpyHostToDevice, s));
-      CK(cudaMemcpyAsync(h->lengths.p, lengths, B * sizeof(int), cudaMemcpyDeviceToDevice, s));
+      CK(cudaMemcpyAsync(h->len_in.p, lengths, B * sizeof(int), cudaMemcpyHostToDevice, s));
+      len_src = h->len_in.as<int>();
     }
+    CK(ie::launch_prep_lengths(len_src, B, T, b_pad, h->lengths.as<int>(), h->err.as<int>(), s));
   }
   const int64_t* ids_dev = ids;
   if (!dev) {
@@ -350,190 +379,138 @@ int run_encoder(ie_encoder* h, const int64_t* ids, const int32_t* lengths, int B
   h->ev_used = 0;
   h->last_T = T;
   h->last_b_pad = b_pad;
-  // layer 0 from the per-token projection table (only the wide / rotating kernels take the token indirection)
-  const bool proj = h->use_proj && (wide || rot) && c.n_layers > 1;
   if (proj && !h->proj_built && (rc = build_proj_table(h, s)) != IE_OK) return rc;
-  if ((rc = mark(h, s)) != IE_OK) return rc;
-  if (proj)
+  if ((rc = mark(h, 0, s)) != IE_OK) return rc;
+  const int ring_mul = h->segs > 1 ? 2 : 1;
+  const long long mop = max_out_pad(h);
+  if (proj) {
     CK(ie::launch_tokens_time_major(ids_dev, B, T, b_pad, c.vocab_sz, c.pad_idx, h->tok.as<int>(), h->err.as<int>(), s));
-  else
-    CK(ie::launch_embed_gather(ids_dev, B, T, b_pad, h->emb.as<__nv_bfloat16>(), c.vocab_sz, h->e_pad,
-                               h->x0.as<__nv_bfloat16>(), h->e_pad, c.pad_idx, h->err.as<int>(), s));
-  h->launches++;
-  if ((rc = mark(h, s)) != IE_OK) return rc;
+    h->launches++;
+  }
+  if (h->use_persistent) check_persistent(h, s);
+  const bool persistent = h->use_persistent != 0;
+  // h_{-1} = 0 for every layer
+  const size_t carry_layer = static_cast<size_t>(h->max_batch) * h->y_ld;  // elements
+  CK(cudaMemsetAsync(h->hcarry.p, 0, static_cast<size_t>(c.n_layers) * carry_layer * sizeof(__nv_bfloat16), s));
+  const size_t slot_bytes = static_cast<size_t>(b_pad) * h->y_ld * sizeof(__nv_bfloat16);
 
-  const long long rows = static_cast<long long>(T) * b_pad;
-  // persistent per-layer recurrent kernel: needs both 128-row halves and every CTA of a layer co-resident
-  bool seq = h->use_seq && b_pad >= 256 && !wide && !rot;
-  if (wide) {
-    if (h->use_wide && !h->wide_checked) {
-      for (const Layer& L : h->layersB) {
-        ie::LstmWideArgs q{};
-        q.T = 1; q.ng = 3; q.u = L.u; q.n_cta = L.n_cta; q.out_pad = L.out_pad; q.kh_pad = L.kh_pad;
-        q.num_sms = h->num_sms; q.check_only = 1;
-        if (ie::launch_lstm_wide(q, s) != cudaSuccess) h->use_wide = 0;
-      }
-      cudaGetLastError();
-      h->wide_checked = 1;
-    }
-    if (!h->use_wide) return fail(IE_ERR_STATE, "B > 512 needs the wide persistent kernel (caller splits the batch)");
-  }
-  if ((seq || wide) && !h->seq_checked) {  // (not needed by the rotating schedule, which runs every layer itself)
-    for (const Layer& L : h->layers) {
-      ie::LstmSeqArgs q{};
-      q.T = 1; q.b_pad = 256; q.u = L.u; q.n_cta = L.n_cta; q.out_pad = L.out_pad; q.kh_pad = L.kh_pad;
-      q.check_only = 1;
-      if (L.n_cta % 2 || ie::launch_lstm_seq(q, s) != cudaSuccess) { h->use_seq = 0; seq = false; }
-    }
-    cudaGetLastError();
-    h->seq_checked = 1;
-  }
-  if (b_pad == 512 && !seq && !rot) return fail(IE_ERR_STATE, "B > 256 needs the persistent kernel (caller splits the batch)");
-  if (seq || wide || rot)
-    CK(cudaMemsetAsync(h->step_done.p, 0, static_cast<size_t>(c.n_layers) * T * kStepStride * sizeof(unsigned), s));
-  // slot 0 of both hidden-state rings is h_{-1} = 0; a previous call with another B_pad may have written these rows
-  for (int i = 0; i < 2; ++i)
-    CK(cudaMemsetAsync(h->y[i].p, 0, static_cast<size_t>(b_pad) * h->y_ld * sizeof(__nv_bfloat16), s));
-  int cur = 0;
-  const __nv_bfloat16* layer_in = h->x0.as<__nv_bfloat16>();
-  long long layer_in_ld = h->e_pad;
-  // with three batches per launch the pooled last layer (narrow, latency bound) still runs the lstm_seq.cu kernel on its
-  // plan-A layout when that is possible; all other layers use the wide tiles of plan B
-  const Layer& lastA = h->layers.back();
-  const bool last_on_seq = wide && !rot && !pool_raw && pooled && raw_out == nullptr && h->use_seq && lastA.u <= 12 && lastA.n_cta % 2 == 0 &&
-                           (c.n_layers < 2 || lastA.kin_pad == h->layersB[c.n_layers - 1].kin_pad);
-  for (int l = 0; l < c.n_layers; ++l) {
-    const bool last = (l == c.n_layers - 1);
-    Layer& L = (last && last_on_seq) ? h->layers[l] : LS[l];
-    // hoisted input projection over all T*b_pad rows
-    ie::GemmArgs g{};
-    g.a = layer_in;
-    g.lda = layer_in_ld;
-    g.b = L.w_ih.as<__nv_bfloat16>();
-    g.ldb = L.kin_pad;
-    g.d = h->gx.p;
-    g.ldd = 4ll * L.out_pad;
-    g.bias = L.bias.as<float>();
-    g.m_pad = static_cast<int>(rows);
-    g.n_pad = 4 * L.out_pad;
-    g.k_pad = L.kin_pad;
-    g.m_store = static_cast<int>(rows);
-    g.n_store = 4 * L.out_pad;
-    g.bn = L.bn;
-    g.act = 0;
-    g.out_bf16 = 0;
-    g.num_sms = h->num_sms;
-    const bool from_table = proj && l == 0;  // Gx rows of layer 0 are rows of the per-token table: no GEMM
-    if (!from_table) {
-      CK(ie::launch_gemm_bf16(g, s));
+  for (long long t0 = 0; t0 < T; t0 += chunk_T) {
+    const int Tc = static_cast<int>(std::min<long long>(chunk_T, T - t0));
+    const long long crow = static_cast<long long>(Tc) * b_pad;
+    if (!proj) {
+      CK(ie::launch_embed_gather(ids_dev, B, T, b_pad, h->emb.as<__nv_bfloat16>(), c.vocab_sz, ring_mul * h->e_pad,
+                                 h->x0.as<__nv_bfloat16>(), ring_mul * h->e_pad, c.pad_idx, h->err.as<int>(),
+                                 static_cast<int>(t0), Tc, s));
       h->launches++;
     }
-    if ((rc = mark(h, s)) != IE_OK) return rc;
+    if ((rc = mark(h, 1, s)) != IE_OK) return rc;
+    int cur = 0;
+    const __nv_bfloat16* layer_in = h->x0.as<__nv_bfloat16>();
+    long long layer_in_ld = ring_mul * h->e_pad;
+    for (int l = 0; l < c.n_layers; ++l) {
+      const bool last = (l == c.n_layers - 1);
+      Layer& L = h->layers[l];
+      const bool from_table = proj && l == 0;  // Gx rows of layer 0 are rows of the per-token table: no GEMM
+      __nv_bfloat16* ybuf = h->y[cur].as<__nv_bfloat16>();
+      __nv_bfloat16* carry = h->hcarry.as<__nv_bfloat16>() + static_cast<size_t>(l) * carry_layer;
+      float* cstate = h->c.as<float>() + static_cast<size_t>(l) * h->max_batch * mop;
+      CUtensorMap tm_h, tm_w;
+      CK(ie::make_tmap_bf16_2d(&tm_h, ybuf, static_cast<uint64_t>(ring_mul) * L.kh_pad, static_cast<uint64_t>(crow + b_pad),
+                               h->y_ld, 64, 128));
+      CK(ie::make_tmap_bf16_2d(&tm_w, L.w_hh.p, static_cast<uint64_t>(ring_mul) * L.kh_pad, 4ull * L.out_pad,
+                               static_cast<uint64_t>(ring_mul) * L.kh_pad, 64, 128));
+      // slot 0 of the ring = this layer's h at the end of the previous chunk (zeros before the first)
+      CK(cudaMemcpyAsync(ybuf, carry, slot_bytes, cudaMemcpyDeviceToDevice, s));
+      if (!from_table) {
+        // hoisted input projection over the chunk's Tc*b_pad rows
+        ie::GemmArgs g{};
+        fill_gemm(h, L, g);
+        g.a = layer_in;
+        g.lda = layer_in_ld;
+        g.d = h->gx.p;
+        g.m_pad = static_cast<int>(crow);
+        g.m_store = static_cast<int>(crow);
+        CK(ie::launch_gemm_bf16(g, s));
+        h->launches++;
+      }
+      if ((rc = mark(h, 2 + 2 * l, s)) != IE_OK) return rc;
 
-    // recurrence
-    ie::LstmStepArgs a{};
-    __nv_bfloat16* ybuf = h->y[cur].as<__nv_bfloat16>();
-    CK(ie::make_tmap_bf16_2d(&a.tm_h, ybuf, L.kh_pad, static_cast<uint64_t>(rows + b_pad), h->y_ld, 64, 128));
-    CK(ie::make_tmap_bf16_2d(&a.tm_w, L.w_hh.p, L.kh_pad, 4ull * L.out_pad, L.kh_pad, 64, 4 * L.u));
-    a.cluster = L.cluster;
-    a.fast_math = h->fast_math;
-    CK(ie::make_tmap_bf16_2d(&a.tm_hs, ybuf, L.kh_pad, static_cast<uint64_t>(rows + b_pad), h->y_ld, 64,
-                             128 / L.cluster));
-    a.gx = from_table ? h->proj.as<float>() : h->gx.as<float>();
-    a.c = h->c.as<float>();
-    a.y = ybuf;
-    a.raw = (last && (raw_out != nullptr || pool_raw)) ? h->raw.as<float>() : nullptr;
-    a.pool_sum = (last && pooled && !pool_raw) ? h->pool_sum.as<float>() : nullptr;
-    a.pool_max = h->pool_max.as<float>();
-    a.pool_last = h->pool_last.as<float>();
-    a.lengths = h->lengths.as<int>();
-    a.T = T;
-    a.b_pad = b_pad;
-    a.u = L.u;
-    a.n_cta = L.n_cta;
-    a.out_pad = L.out_pad;
-    a.kh_pad = L.kh_pad;
-    a.ldy = h->y_ld;
-    a.raw_ld = L.out_pad;
-    if (rot) {
-      ie::LstmWideArgs q{};
-      q.tm_h = a.tm_h; q.tm_w = a.tm_w; q.gx = a.gx; q.c = a.c; q.y = a.y; q.raw = a.raw;
-      q.pool_sum = a.pool_sum; q.pool_max = a.pool_max; q.pool_last = a.pool_last; q.lengths = a.lengths;
-      q.step_done = h->step_done.as<unsigned>() + static_cast<size_t>(l) * T * kStepStride;
-      q.T = T; q.ng = b_pad / 256; q.u = L.u; q.n_cta = L.n_cta; q.out_pad = L.out_pad; q.kh_pad = L.kh_pad;
-      q.ldy = a.ldy; q.raw_ld = a.raw_ld; q.fast_math = h->fast_math; q.num_sms = h->num_sms; q.check_only = 0;
-      q.trace = nullptr;
-      q.variant = h->rot_variant;
-      q.tok = from_table ? h->tok.as<int>() : nullptr;
-      if (l == h->trace_layer) {
-        const int pairs = ie::lstm_rot_pairs(q);
-        const long long items = (static_cast<long long>(T) * q.ng * (L.n_cta / 2) + pairs - 1) / pairs;
-        CK(h->trace.reserve(static_cast<size_t>(2 * pairs) * items * 12 * sizeof(long long), true));
-        q.trace = h->trace.as<long long>();
-        q.trace_items = static_cast<int>(items);
-        h->trace_T = static_cast<int>(items);
-        h->trace_ctas = 2 * pairs;
+      if (persistent) {
+        CK(cudaMemsetAsync(h->step_done.p, 0, static_cast<size_t>(Tc) * ng * sizeof(unsigned), s));
+        ie::LstmLayerArgs q{};
+        q.tm_h = tm_h; q.tm_w = tm_w;
+        q.gx = from_table ? h->proj.p : h->gx.p;
+        q.tok = from_table ? h->tok.as<int>() : nullptr;
+        q.c = cstate; q.y = ybuf;
+        q.raw = (last && raw_out != nullptr) ? h->raw.as<float>() : nullptr;
+        q.pool_sum = (last && pooled) ? h->pool_sum.as<float>() : nullptr;
+        q.pool_max = h->pool_max.as<float>(); q.pool_last = h->pool_last.as<float>();
+        q.lengths = h->lengths.as<int>();
+        q.step_done = h->step_done.as<unsigned>();
+        q.abort_flag = h->err.as<unsigned>() + 1; q.spin_limit = h->spin_limit;
+        q.T = Tc; q.t0 = static_cast<int>(t0); q.T_total = T; q.ng = ng;
+        q.u = L.u; q.n_cta = L.n_cta; q.out_pad = L.out_pad; q.kh_pad = L.kh_pad;
+        q.ldy = h->y_ld; q.raw_ld = L.out_pad;
+        q.gate_mode = h->gate_mode; q.gx_bf16 = h->gx_bf16; q.segs = h->segs;
+        q.num_sms = h->num_sms; q.check_only = 0; q.cooperative = h->cooperative; q.fault = h->fault;
+        q.diag = h->diag.as<long long>() + 4 * l;
+        q.trace = nullptr;
+        if (l == h->trace_layer && t0 == 0) {
+          const int pairs = ie::lstm_layer_pairs(q);
+          const long long items = (static_cast<long long>(Tc) * ng * (L.n_cta / 2) + pairs - 1) / pairs;
+          CK(h->trace.reserve(static_cast<size_t>(2 * pairs) * items * 12 * sizeof(long long), true));
+          q.trace = h->trace.as<long long>();
+          q.trace_items = static_cast<int>(items);
+          h->trace_T = static_cast<int>(items);
+          h->trace_ctas = 2 * pairs;
+        }
+        cudaError_t e = ie::launch_lstm_layer(q, s);
+        if (e == cudaErrorCooperativeLaunchTooLarge) {
+          cudaGetLastError();
+          return fail(IE_ERR_STATE, "the persistent recurrent kernel cannot be co-resident on this device "
+                                   "(cooperative launch refused); set IE_SEQ=0 for the per-timestep fallback");
+        }
+        CK(e);
+        h->launches += 1;
+      } else {
+        ie::LstmStepArgs a{};
+        a.tm_h = tm_h; a.tm_w = tm_w;
+        a.gx = from_table ? h->proj.p : h->gx.p;
+        a.tok = from_table ? h->tok.as<int>() : nullptr;
+        a.c = cstate; a.y = ybuf;
+        a.raw = (last && raw_out != nullptr) ? h->raw.as<float>() : nullptr;
+        a.pool_sum = (last && pooled) ? h->pool_sum.as<float>() : nullptr;
+        a.pool_max = h->pool_max.as<float>(); a.pool_last = h->pool_last.as<float>();
+        a.lengths = h->lengths.as<int>();
+        a.abort_flag = h->err.as<unsigned>() + 1; a.spin_limit = h->spin_limit;
+        a.t0 = static_cast<int>(t0); a.T_total = T; a.b_pad = b_pad;
+        a.u = L.u; a.n_cta = L.n_cta; a.out_pad = L.out_pad; a.kh_pad = L.kh_pad;
+        a.ldy = h->y_ld; a.raw_ld = L.out_pad;
+        a.gate_mode = h->gate_mode; a.gx_bf16 = h->gx_bf16; a.segs = h->segs;
+        for (int t = 0; t < Tc; ++t)
+          for (int g = 0; g < ng; ++g) {
+            a.t = t; a.g = g;
+            CK(ie::launch_lstm_step(a, s));
+          }
+        h->launches += static_cast<int64_t>(Tc) * ng;
       }
-      CK(ie::launch_lstm_rot(q, s));
-      h->launches += 1;
-    } else if (wide && !(last && last_on_seq)) {
-      ie::LstmWideArgs q{};
-      q.tm_h = a.tm_h; q.tm_w = a.tm_w; q.gx = a.gx; q.c = a.c; q.y = a.y; q.raw = a.raw;
-      q.pool_sum = a.pool_sum; q.pool_max = a.pool_max; q.pool_last = a.pool_last; q.lengths = a.lengths;
-      q.step_done = h->step_done.as<unsigned>() + static_cast<size_t>(l) * T * kStepStride;
-      q.T = T; q.ng = 3; q.u = L.u; q.n_cta = L.n_cta; q.out_pad = L.out_pad; q.kh_pad = L.kh_pad;
-      q.ldy = a.ldy; q.raw_ld = a.raw_ld; q.fast_math = h->fast_math; q.num_sms = h->num_sms; q.check_only = 0;
-      q.trace = nullptr;
-      q.tok = from_table ? h->tok.as<int>() : nullptr;
-      if (l == h->trace_layer) {
-        const int grid = 2 * std::min(h->num_sms / 2, 3 * (L.n_cta / 2));
-        CK(h->trace.reserve(static_cast<size_t>(grid) * T * 12 * sizeof(long long), true));
-        q.trace = h->trace.as<long long>();
-        h->trace_T = T;
-        h->trace_ctas = grid;
-      }
-      CK(ie::launch_lstm_wide(q, s));
-      h->launches += 1;
-    } else if (seq || (last && last_on_seq)) {
-      ie::LstmSeqArgs q{};
-      q.tm_h = a.tm_h; q.tm_w = a.tm_w; q.gx = a.gx; q.y = a.y; q.raw = a.raw;
-      q.pool_sum = a.pool_sum; q.pool_max = a.pool_max; q.pool_last = a.pool_last; q.lengths = a.lengths;
-      q.step_done = h->step_done.as<unsigned>() + static_cast<size_t>(l) * T * kStepStride;
-      q.T = T; q.b_pad = b_pad; q.u = L.u; q.n_cta = L.n_cta; q.out_pad = L.out_pad; q.kh_pad = L.kh_pad;
-      q.ldy = a.ldy; q.raw_ld = a.raw_ld; q.check_only = 0;
-      q.fast_math = h->fast_math;
-      q.trace = nullptr;
-      if (l == h->trace_layer) {
-        CK(h->trace.reserve(static_cast<size_t>(L.n_cta) * T * 12 * sizeof(long long), true));
-        q.trace = h->trace.as<long long>();
-        h->trace_T = T;
-        h->trace_ctas = L.n_cta;
-      }
-      CK(ie::launch_lstm_seq(q, s));
-      h->launches += 1;
-    } else {
-      for (int t = 0; t < T; ++t) {
-        a.t = t;
-        CK(ie::launch_lstm_step(a, s));
-      }
-      h->launches += T;
+      if (t0 + Tc < T)  // carry h of the chunk's last step into the next chunk
+        CK(cudaMemcpyAsync(carry, ybuf + static_cast<size_t>(Tc) * b_pad * h->y_ld, slot_bytes, cudaMemcpyDeviceToDevice, s));
+      if ((rc = mark(h, 3 + 2 * l, s)) != IE_OK) return rc;
+      layer_in = ybuf + static_cast<long long>(b_pad) * h->y_ld;  // slot 1 onwards
+      layer_in_ld = h->y_ld;
+      cur ^= 1;
     }
-    if ((rc = mark(h, s)) != IE_OK) return rc;
-    layer_in = ybuf + static_cast<long long>(b_pad) * h->y_ld;  // slot 1 onwards
-    layer_in_ld = h->y_ld;
-    cur ^= 1;
   }
+  const long long rows = static_cast<long long>(T) * b_pad;
 
-  const Layer& LL = (last_on_seq && !rot) ? h->layers.back() : LS.back();
+  const Layer& LL = h->layers.back();
   if (pooled) {
     float* out_dev = dev ? out : h->out.as<float>();
-    if (pool_raw)
-      CK(ie::launch_pool_from_raw(h->raw.as<float>(), h->lengths.as<int>(), B, T, c.emb_sz, LL.out_pad, out_dev, s));
-    else
-      CK(ie::launch_pool_finalize(h->pool_sum.as<float>(), h->pool_max.as<float>(), h->pool_last.as<float>(),
-                                  h->lengths.as<int>(), B, c.emb_sz, LL.out_pad, out_dev, s));
+    CK(ie::launch_pool_finalize(h->pool_sum.as<float>(), h->pool_max.as<float>(), h->pool_last.as<float>(),
+                                h->lengths.as<int>(), B, c.emb_sz, LL.out_pad, out_dev, s));
     h->launches++;
-    if ((rc = mark(h, s)) != IE_OK) return rc;
+    if ((rc = mark(h, 2 + 2 * c.n_layers, s)) != IE_OK) return rc;
     if (!dev)
       CK(cudaMemcpyAsync(out, out_dev, static_cast<size_t>(B) * 3 * c.emb_sz * sizeof(float), cudaMemcpyDeviceToHost, s));
   }
@@ -543,15 +520,36 @@ int run_encoder(ie_encoder* h, const int64_t* ids, const int32_t* lengths, int B
                          static_cast<size_t>(LL.out_pad) * sizeof(float), static_cast<size_t>(c.emb_sz) * sizeof(float),
                          static_cast<size_t>(B) * T, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
   }
-  if (!dev) {
-    int err_host = 0;
-    CK(cudaMemcpyAsync(&err_host, h->err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    if (err_host != 0) {
-      cudaMemsetAsync(h->err.p, 0, sizeof(int), s);
-      return fail(IE_ERR_TOKEN, "token id outside [0,%d) in ids", c.vocab_sz);
+  CK(cudaEventRecord(h->done_ev, s));
+  h->has_done = true;
+  h->last_stream = s;
+  // a handle that once served a very long sequence does not keep tens of GB for ever
+  if (h->ws_tokens > (1ll << 20) && std::min<long long>(rows, chunk_T * b_pad) * 8 < h->ws_tokens) {
+    if (++h->small_calls >= 4) {
+      CK(cudaStreamSynchronize(s));
+      release_workspace(h);
     }
+  } else {
+    h->small_calls = 0;
   }
+  return IE_OK;
+}
+
+// read and clear the device error words of the last call (waits for it)
+int collect_errors(ie_encoder* h) {
+  if (!h->has_done) return IE_OK;
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaEventSynchronize(h->done_ev));
+  int w[kErrWords] = {0, 0, 0, 0};
+  CK(cudaMemcpy(w, h->err.p, sizeof(w), cudaMemcpyDeviceToHost));
+  if (w[0] | w[1] | w[2]) CK(cudaMemset(h->err.p, 0, sizeof(w)));
+  if (w[1] != 0) {
+    h->use_persistent = h->fault ? h->use_persistent : 0;  // do not walk into the same wall again
+    return fail(IE_ERR_CUDA, "a device-side wait exceeded its limit and the kernel was drained (the persistent grid lost "
+                             "co-residency, or a protocol error); results of this call are invalid");
+  }
+  if (w[0] != 0) return fail(IE_ERR_TOKEN, "token id outside [0,%d) in ids", h->cfg.vocab_sz);
+  if (w[2] != 0) return fail(IE_ERR_INVALID, "a length outside [1,T] was clamped");
   return IE_OK;
 }
 
@@ -559,7 +557,7 @@ int run_encoder(ie_encoder* h, const int64_t* ids, const int32_t* lengths, int B
 
 extern "C" {
 
-int ie_version(void) { return 100; }
+int ie_version(void) { return 200; }
 
 const char* ie_last_error(void) { return g_last_error.c_str(); }
 
@@ -582,21 +580,26 @@ int ie_encoder_create(const ie_config* cfg, ie_encoder** out) {
   ie_encoder* h = new ie_encoder();
   h->cfg = *cfg;
   h->num_sms = sms;
-  if (const char* e = getenv("IE_SEQ")) h->use_seq = atoi(e);
-  if (const char* e = getenv("IE_ROT")) h->use_rot = atoi(e);
-  if (const char* e = getenv("IE_ROT_VARIANT")) h->rot_variant = atoi(e) & 3;
-  if (const char* e = getenv("IE_EMB_PROJ")) h->use_proj = atoi(e);
-  if (const char* e = getenv("IE_POOL_RAW")) h->use_pool_raw = atoi(e);
-  if (h->use_rot) {
-    // five batches put an item's inputs two rounds back (C = 190 >= 2*74 + 38); IE_ROT_BATCHES=6..8 buys more slack
-    int nb = 5;
-    if (const char* e = getenv("IE_ROT_BATCHES")) nb = std::min(ie::kRotMaxBatches, std::max(1, atoi(e)));
-    h->max_batch = std::max(IE_MAX_BATCH, 256 * nb);
+  if (cfg->flags & IE_CFG_FP32) {  // split-bf16 products (~fp32), f32 Gx, IEEE gates
+    h->segs = 3;
+    h->gx_bf16 = 0;
+    h->gate_mode = 0;
+  } else {
+    h->gate_mode = (cfg->flags & IE_CFG_ACCURATE_GATES) ? 1 : 2;
+    if (cfg->flags & IE_CFG_F32_GX) h->gx_bf16 = 0;
   }
-  h->fast_math = (cfg->flags & IE_CFG_ACCURATE_GATES) ? 0 : 1;
-  if (const char* e = getenv("IE_FAST_MATH")) h->fast_math = atoi(e);
-  int rc = plan_layers(h, h->layers, 0);
-  if (rc == IE_OK) rc = plan_layers(h, h->layersB, 32);
+  // development knobs; none is needed in production
+  if (const char* v = getenv("IE_SEQ")) h->use_persistent = atoi(v);
+  if (const char* v = getenv("IE_COOP")) h->cooperative = atoi(v);
+  if (const char* v = getenv("IE_EMB_PROJ")) h->use_proj = atoi(v);
+  if (const char* v = getenv("IE_GX_BF16")) { if (h->segs == 1) h->gx_bf16 = atoi(v); }
+  if (const char* v = getenv("IE_FAST_MATH")) { if (h->segs == 1) h->gate_mode = atoi(v) ? 2 : 1; }
+  if (const char* v = getenv("IE_BATCHES")) h->batches = std::min(ie::kMaxBatches, std::max(1, atoi(v)));
+  if (const char* v = getenv("IE_SPIN_LIMIT_MS")) h->spin_limit = static_cast<long long>(atof(v) * 1.9e6);
+  if (const char* v = getenv("IE_DEBUG_FAULT")) h->fault = atoi(v);
+  if (const char* v = getenv("IE_CHUNK_T")) h->chunk_t = atoll(v);
+  h->max_batch = 256 * h->batches;
+  int rc = plan_layers(h);
   if (rc != IE_OK) { delete h; return rc; }
   e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) { delete h; return cuda_fail(e, "cudaStreamCreate"); }
@@ -609,11 +612,12 @@ void ie_encoder_destroy(ie_encoder* h) {
   cudaSetDevice(h->cfg.device);
   cudaDeviceSynchronize();
   for (Layer& L : h->layers) { L.w_ih.release(); L.w_hh.release(); L.bias.release(); }
-  for (Layer& L : h->layersB) { L.w_ih.release(); L.w_hh.release(); L.bias.release(); }
-  DevBuf* bufs[] = {&h->emb, &h->ids, &h->lengths, &h->x0, &h->y[0], &h->y[1], &h->gx, &h->c, &h->pool_sum,
-                    &h->pool_max, &h->pool_last, &h->out, &h->raw, &h->err, &h->step_done, &h->trace, &h->proj, &h->tok};
+  DevBuf* bufs[] = {&h->emb, &h->ids, &h->len_in, &h->lengths, &h->x0, &h->y[0], &h->y[1], &h->gx, &h->c, &h->pool_sum,
+                    &h->pool_max, &h->pool_last, &h->out, &h->raw, &h->err, &h->step_done, &h->trace, &h->proj, &h->tok,
+                    &h->diag, &h->hcarry};
   for (DevBuf* b : bufs) b->release();
   for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
+  if (h->done_ev) cudaEventDestroy(h->done_ev);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
 }
@@ -622,11 +626,11 @@ int ie_encoder_load_embedding(ie_encoder* h, const float* emb) {
   if (h == nullptr || emb == nullptr) return fail(IE_ERR_INVALID, "null argument");
   std::lock_guard<std::mutex> lk(h->mu);
   CK(cudaSetDevice(h->cfg.device));
-  // IE_EMB_PROJ: the table GEMM reads the embedding as its A operand, so its rows are padded to whole M tiles (zeros)
-  const int v_rows = h->use_proj ? static_cast<int>(round_up(h->cfg.vocab_sz, 256)) : h->cfg.vocab_sz;
+  // the per-token table GEMM reads the embedding as its A operand: rows padded to whole M tiles (zeros)
+  const int v_rows = static_cast<int>(round_up(h->cfg.vocab_sz, 256));
   std::vector<int> ident(v_rows);
   for (int i = 0; i < v_rows; ++i) ident[i] = i < h->cfg.vocab_sz ? i : -1;
-  int rc = upload_sliced(emb, h->cfg.vocab_sz, h->cfg.emb_sz, ident, h->e_pad, h->emb, h->own_stream);
+  int rc = upload_sliced(emb, h->cfg.vocab_sz, h->cfg.emb_sz, ident, h->e_pad, h->segs, h->emb, h->own_stream);
   if (rc != IE_OK) return rc;
   h->emb_loaded = true;
   h->proj_built = false;
@@ -640,56 +644,19 @@ int ie_encoder_load_layer(ie_encoder* h, int32_t layer, const float* w_ih, const
   if (layer < 0 || layer >= h->cfg.n_layers) return fail(IE_ERR_INVALID, "layer %d out of range", layer);
   std::lock_guard<std::mutex> lk(h->mu);
   CK(cudaSetDevice(h->cfg.device));
-  for (std::vector<Layer>* plan : {&h->layers, &h->layersB}) {  // both weight layouts stay resident (2 x 266 MB at R4)
-    Layer& L = (*plan)[layer];
-    const std::vector<int> perm = slice_perm(L);
-    int rc = upload_sliced(w_ih, 4 * L.out, L.in, perm, L.kin_pad, L.w_ih, h->own_stream);
-    if (rc != IE_OK) return rc;
-    rc = upload_sliced(w_hh, 4 * L.out, L.out, perm, L.kh_pad, L.w_hh, h->own_stream);
-    if (rc != IE_OK) return rc;
-    std::vector<float> bias(perm.size());
-    for (size_t r = 0; r < perm.size(); ++r) bias[r] = perm[r] < 0 ? 0.0f : b_ih[perm[r]] + b_hh[perm[r]];
-    CK(L.bias.reserve(bias.size() * sizeof(float)));
-    CK(cudaMemcpy(L.bias.p, bias.data(), bias.size() * sizeof(float), cudaMemcpyHostToDevice));
-    L.loaded = true;
-  }
+  Layer& L = h->layers[layer];
+  const std::vector<int> perm = slice_perm(L);
+  int rc = upload_sliced(w_ih, 4 * L.out, L.in, perm, L.kin_pad, h->segs, L.w_ih, h->own_stream);
+  if (rc != IE_OK) return rc;
+  rc = upload_sliced(w_hh, 4 * L.out, L.out, perm, L.kh_pad, h->segs, L.w_hh, h->own_stream);
+  if (rc != IE_OK) return rc;
+  std::vector<float> bias(perm.size());
+  for (size_t r = 0; r < perm.size(); ++r) bias[r] = perm[r] < 0 ? 0.0f : b_ih[perm[r]] + b_hh[perm[r]];
+  CK(L.bias.reserve(bias.size() * sizeof(float)));
+  CK(cudaMemcpy(L.bias.p, bias.data(), bias.size() * sizeof(float), cudaMemcpyHostToDevice));
+  L.loaded = true;
   if (layer == 0) h->proj_built = false;
   return IE_OK;
-}
-
-// rows beyond what the available persistent kernels take in one launch are run as consecutive sub-batches
-static int encode_locked(ie_encoder* h, const int64_t* ids, const int32_t* lengths, int B, int T, float* out, int flags,
-                         cudaStream_t s) {
-  const long long ow = 3ll * h->cfg.emb_sz;
-  if (B > IE_MAX_BATCH) {  // only reachable with the experimental rotating schedule (max_batch > IE_MAX_BATCH)
-    if (h->use_rot) {
-      const int rc = run_encoder(h, ids, lengths, B, T, out, nullptr, flags, s);
-      if (rc != IE_ERR_STATE || h->use_rot) return rc;
-    }
-    const int rc = encode_locked(h, ids, lengths, IE_MAX_BATCH, T, out, flags, s);
-    if (rc != IE_OK) return rc;
-    return encode_locked(h, ids + static_cast<long long>(IE_MAX_BATCH) * T, lengths + IE_MAX_BATCH, B - IE_MAX_BATCH, T,
-                         out + IE_MAX_BATCH * ow, flags, s);
-  }
-  if (B > 512) {
-    if (h->use_wide) {
-      const int rc = run_encoder(h, ids, lengths, B, T, out, nullptr, flags, s);
-      if (rc != IE_ERR_STATE || h->use_wide) return rc;
-    }
-    const int rc = encode_locked(h, ids, lengths, 512, T, out, flags, s);
-    if (rc != IE_OK) return rc;
-    return encode_locked(h, ids + 512ll * T, lengths + 512, B - 512, T, out + 512 * ow, flags, s);
-  }
-  if (B > 256) {
-    if (h->use_seq) {
-      const int rc = run_encoder(h, ids, lengths, B, T, out, nullptr, flags, s);
-      if (rc != IE_ERR_STATE || h->use_seq) return rc;
-    }
-    const int rc = encode_locked(h, ids, lengths, 256, T, out, flags, s);
-    if (rc != IE_OK) return rc;
-    return encode_locked(h, ids + 256ll * T, lengths + 256, B - 256, T, out + 256 * ow, flags, s);
-  }
-  return run_encoder(h, ids, lengths, B, T, out, nullptr, flags, s);
 }
 
 int ie_encoder_encode(ie_encoder* h, const int64_t* ids, const int32_t* lengths, int32_t B, int32_t T, float* out,
@@ -697,12 +664,14 @@ int ie_encoder_encode(ie_encoder* h, const int64_t* ids, const int32_t* lengths,
   if (h == nullptr) return fail(IE_ERR_INVALID, "null handle");
   if (out == nullptr) return fail(IE_ERR_INVALID, "out is null");
   if (ids == nullptr || lengths == nullptr) return fail(IE_ERR_INVALID, "null pointer");
-  if (B < 1 || B > h->max_batch) return fail(IE_ERR_INVALID, "B=%d outside [1,%d]", B, h->max_batch);
   std::lock_guard<std::mutex> lk(h->mu);
   // device-pointer mode: `stream` is used verbatim (NULL = the legacy default stream, e.g. torch's default);
   // host-pointer mode: NULL selects the handle's own stream
-  cudaStream_t s = (stream || (flags & IE_FLAG_DEVICE_PTRS)) ? static_cast<cudaStream_t>(stream) : h->own_stream;
-  return encode_locked(h, ids, lengths, B, T, out, flags, s);
+  const bool dev = (flags & IE_FLAG_DEVICE_PTRS) != 0;
+  cudaStream_t s = (stream || dev) ? static_cast<cudaStream_t>(stream) : h->own_stream;
+  int rc = run_encoder(h, ids, lengths, B, T, out, nullptr, flags, s);
+  if (rc != IE_OK || dev) return rc;
+  return collect_errors(h);  // host-pointer mode: synchronous, device-side errors are reported by this call
 }
 
 int ie_encoder_raw_features(ie_encoder* h, const int64_t* ids, int32_t B, int32_t T, float* raw, int32_t flags,
@@ -710,16 +679,25 @@ int ie_encoder_raw_features(ie_encoder* h, const int64_t* ids, int32_t B, int32_
   if (h == nullptr) return fail(IE_ERR_INVALID, "null handle");
   if (raw == nullptr) return fail(IE_ERR_INVALID, "raw is null");
   std::lock_guard<std::mutex> lk(h->mu);
-  cudaStream_t s = (stream || (flags & IE_FLAG_DEVICE_PTRS)) ? static_cast<cudaStream_t>(stream) : h->own_stream;
-  return run_encoder(h, ids, nullptr, B, T, nullptr, raw, flags, s);
+  const bool dev = (flags & IE_FLAG_DEVICE_PTRS) != 0;
+  cudaStream_t s = (stream || dev) ? static_cast<cudaStream_t>(stream) : h->own_stream;
+  int rc = run_encoder(h, ids, nullptr, B, T, nullptr, raw, flags, s);
+  if (rc != IE_OK || dev) return rc;
+  return collect_errors(h);
+}
+
+int ie_encoder_check_errors(ie_encoder* h) {
+  if (h == nullptr) return fail(IE_ERR_INVALID, "null handle");
+  std::lock_guard<std::mutex> lk(h->mu);
+  return collect_errors(h);
 }
 
 int64_t ie_encoder_launch_count(const ie_encoder* h) { return h ? h->launches : 0; }
 
 int32_t ie_encoder_max_batch(const ie_encoder* h) { return h ? h->max_batch : IE_MAX_BATCH; }
 
-// debug: request a per-step timeline of `layer` in the persistent kernel on the next encode (layer < 0: off);
-// with out != NULL copy the last recorded timeline [n_cta][T][8] (SM clocks) and return n_cta*T
+// debug: request a per-item timeline of `layer` in the persistent kernel on the next encode (layer < 0: off);
+// with out != NULL copy the last recorded timeline [ctas][items][12] and return ctas*items
 int64_t ie_debug_seq_trace(ie_encoder* h, int32_t layer, long long* out, int64_t cap) {
   if (h == nullptr) return fail(IE_ERR_INVALID, "null handle");
   std::lock_guard<std::mutex> lk(h->mu);
@@ -740,17 +718,31 @@ int ie_encoder_last_phase_ms(ie_encoder* h, float* ms, int32_t cap) {
   if (h->ev_used < 2) return fail(IE_ERR_STATE, "no encode call recorded");
   CK(cudaSetDevice(h->cfg.device));
   CK(cudaEventSynchronize(h->ev[h->ev_used - 1]));
-  const int n = h->ev_used - 1;
-  for (int i = 0; i < n && i < cap; ++i) CK(cudaEventElapsedTime(&ms[i], h->ev[i], h->ev[i + 1]));
+  const int n = 2 + 2 * h->cfg.n_layers;  // gather, (gemm_l, steps_l) x L, finalize
+  std::vector<float> acc(n, 0.0f);
+  for (int i = 1; i < h->ev_used; ++i) {
+    float t = 0.0f;
+    CK(cudaEventElapsedTime(&t, h->ev[i - 1], h->ev[i]));
+    const int tag = h->ev_tag[i];
+    if (tag >= 1 && tag <= n) acc[tag - 1] += t;  // time chunks of a layer add up
+  }
+  for (int i = 0; i < n && i < cap; ++i) ms[i] = acc[i];
   return n;
 }
 
-// debug: cycles to issue / execute iters*4 tcgen05.mma of shape M=128 (mode 0) or M=256 CTA pair (mode 1) x N=n x K=16
-int ie_debug_umma_rate(int32_t mode, int32_t n, int32_t iters, int32_t commit_every, int32_t grid, int32_t ntiles,
-                       long long* out2) {
-  if (out2 == nullptr || n < 16 || n > 256 || n % 16 || iters < 1) return fail(IE_ERR_INVALID, "bad argument");
-  CK(ie::run_umma_rate(mode, n, iters, commit_every, grid < 1 ? 1 : grid, ntiles, out2));
-  return IE_OK;
+int ie_encoder_last_phase_mhz(ie_encoder* h, float* mhz, int32_t cap) {
+  if (h == nullptr || mhz == nullptr) return fail(IE_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (!h->has_done) return fail(IE_ERR_STATE, "no encode call recorded");
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaEventSynchronize(h->done_ev));
+  std::vector<long long> d(static_cast<size_t>(h->cfg.n_layers) * 4);
+  CK(cudaMemcpy(d.data(), h->diag.p, d.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+  for (int l = 0; l < h->cfg.n_layers && l < cap; ++l) {
+    const long long dc = d[4 * l + 2] - d[4 * l], dn = d[4 * l + 3] - d[4 * l + 1];
+    mhz[l] = dn > 0 ? static_cast<float>(1e3 * static_cast<double>(dc) / static_cast<double>(dn)) : 0.0f;
+  }
+  return h->cfg.n_layers;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -805,7 +797,7 @@ int ie_mlp_load_layer(ie_mlp* m, int32_t layer, const float* coef, const float* 
     for (int o = 0; o < fan_out; ++o) wt[static_cast<size_t>(o) * fan_in + i] = coef[static_cast<size_t>(i) * fan_out + o];
   std::vector<int> perm(L.n_pad);
   for (int r = 0; r < L.n_pad; ++r) perm[r] = r < fan_out ? r : -1;
-  int rc = upload_sliced(wt.data(), fan_out, fan_in, perm, L.k_pad, L.w, m->own_stream);
+  int rc = upload_sliced(wt.data(), fan_out, fan_in, perm, L.k_pad, 1, L.w, m->own_stream);
   if (rc != IE_OK) return rc;
   std::vector<float> b(L.n_pad, 0.0f);
   std::copy(intercept, intercept + fan_out, b.begin());
@@ -841,7 +833,7 @@ int ie_mlp_predict_proba(ie_mlp* m, const float* X, int32_t n, float* probs, int
       xsrc = m->xf.as<float>();
     }
     // f32 -> bf16, K padded with zeros (rows beyond `rows` keep stale finite data; they are never stored)
-    CK(ie::launch_convert_rows(xsrc, d_in, d_in, nullptr, rows, m->act[0].as<__nv_bfloat16>(), m->act_ld, s));
+    CK(ie::launch_convert_rows(xsrc, d_in, d_in, nullptr, rows, m->act[0].as<__nv_bfloat16>(), m->act_ld, 0, s));
     int cur = 0;
     for (int l = 0; l < nl; ++l) {
       const ie_mlp::L& L = m->layers[l];
@@ -913,8 +905,8 @@ int ie_debug_gemm(const float* a, const float* b, const float* bias, int32_t M, 
   CK(dd.reserve(static_cast<size_t>(m_pad) * n_pad * 4));
   CK(cudaMemcpy(fa.p, a, static_cast<size_t>(M) * K * 4, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(fb.p, b, static_cast<size_t>(N) * K * 4, cudaMemcpyHostToDevice));
-  CK(ie::launch_convert_rows(fa.as<float>(), K, K, nullptr, M, ba.as<__nv_bfloat16>(), k_pad, s));
-  CK(ie::launch_convert_rows(fb.as<float>(), K, K, nullptr, N, bb.as<__nv_bfloat16>(), k_pad, s));
+  CK(ie::launch_convert_rows(fa.as<float>(), K, K, nullptr, M, ba.as<__nv_bfloat16>(), k_pad, 0, s));
+  CK(ie::launch_convert_rows(fb.as<float>(), K, K, nullptr, N, bb.as<__nv_bfloat16>(), k_pad, 0, s));
   if (bias) {
     std::vector<float> bp(n_pad, 0.0f);
     std::copy(bias, bias + N, bp.begin());

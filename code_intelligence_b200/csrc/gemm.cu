@@ -31,7 +31,8 @@ template <typename OutT, int ACT>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, OutT* __restrict__ D,
                  const float* __restrict__ bias, int m_store, int n_store, long long ldd, int num_m_blocks,
-                 int num_n_blocks, int num_k_blocks, int bn, int stages, int panel) {
+                 int num_n_blocks, int num_k_blocks, int bn, int stages, int panel, int segs, int k_pad,
+                 unsigned* abort_flag, long long spin_limit) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
@@ -45,6 +46,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tfull_bar = bars + 2 * stages;
   uint64_t* tempty_bar = bars + 2 * stages + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * stages + 4);
+  uint32_t* abort_s = tmem_slot + 1;
+  const Abort ab{abort_s, abort_flag, spin_limit};
+  const int nkt = num_k_blocks * segs;  // split-bf16: K loop over [A_hi | A_lo | A_hi] x [B_hi | B_hi | B_lo]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -62,6 +66,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(&tfull_bar[a], 1);
       mbar_init(&tempty_bar[a], 128);
     }
+    *abort_s = 0;
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 512);
@@ -87,15 +92,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = blockIdx.x; tile < num_tiles && !aborted(ab); tile += gridDim.x) {
         int m_blk, n_blk;
         decode(tile, m_blk, n_blk);
-        for (int kb = 0; kb < num_k_blocks; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+        for (int kb = 0; kb < nkt; ++kb) {
+          const int seg = kb / num_k_blocks, r = kb - seg * num_k_blocks;
+          mbar_wait(&empty_bar[stage], phase ^ 1, ab);
           uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
           mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
-          tma_load_2d(sa, &tmA, &full_bar[stage], kb * kBlockK, m_blk * kBlockM, kEvictNormal);
-          tma_load_2d(sa + a_bytes, &tmB, &full_bar[stage], kb * kBlockK, n_blk * bn, kEvictLast);
+          tma_load_2d(sa, &tmA, &full_bar[stage], (seg == 1 ? k_pad : 0) + r * kBlockK, m_blk * kBlockM, kEvictNormal);
+          tma_load_2d(sa + a_bytes, &tmB, &full_bar[stage], (seg == 2 ? k_pad : 0) + r * kBlockK, n_blk * bn, kEvictLast);
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -107,12 +113,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      for (int tile = blockIdx.x; tile < num_tiles && !aborted(ab); tile += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1, ab);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * bn);
-        for (int kb = 0; kb < num_k_blocks; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
+        for (int kb = 0; kb < nkt; ++kb) {
+          mbar_wait(&full_bar[stage], phase, ab);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
           const uint64_t da = umma_desc_sw128(sa);
@@ -136,7 +142,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       int m_blk, n_blk;
       decode(tile, m_blk, n_blk);
-      mbar_wait(&tfull_bar[acc], acc_phase);
+      mbar_wait(&tfull_bar[acc], acc_phase, ab);
       tc_fence_after();
       const int row = m_blk * kBlockM + q * 32 + lane;
       const bool row_ok = row < m_store;
@@ -195,7 +201,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       OutT* __restrict__ D, const float* __restrict__ bias, int m_store, int n_store, long long ldd,
                       int num_m_blocks /* of 256 rows */, int num_n_blocks, int num_k_blocks, int bn, int stages,
-                      int panel) {
+                      int panel, int segs, int k_pad, unsigned* abort_flag, long long spin_limit) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
@@ -209,6 +215,9 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   uint64_t* tfull_bar = bars + 2 * stages;     // per CTA
   uint64_t* tempty_bar = bars + 2 * stages + 2;  // leader's copy is live: one arrival per CTA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * stages + 4);
+  uint32_t* abort_s = tmem_slot + 1;
+  const Abort ab{abort_s, abort_flag, spin_limit};
+  const int nkt = num_k_blocks * segs;  // split-bf16: K loop over [A_hi | A_lo | A_hi] x [B_hi | B_hi | B_lo]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -229,6 +238,7 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       mbar_init(&tfull_bar[a], 1);
       mbar_init(&tempty_bar[a], 2);
     }
+    *abort_s = 0;
     fence_barrier_init();
   }
   cluster_sync();
@@ -253,17 +263,18 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      for (int tile = pair; tile < num_tiles && !aborted(ab); tile += num_pairs) {
         int m_blk, n_blk;
         decode(tile, m_blk, n_blk);
-        for (int kb = 0; kb < num_k_blocks; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+        for (int kb = 0; kb < nkt; ++kb) {
+          const int seg = kb / num_k_blocks, r = kb - seg * num_k_blocks;
+          mbar_wait(&empty_bar[stage], phase ^ 1, ab);
           uint8_t* sa = smem + static_cast<size_t>(stage) * stage_bytes;
           if (crank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * stage_bytes);
           else mbar_arrive_remote(&full_bar[stage], 0);
-          tma_load_2d_pair(sa, &tmA, &full_bar[stage], kb * kBlockK, m_blk * 256 + static_cast<int>(crank) * kBlockM,
-                           kEvictNormal);
-          tma_load_2d_pair(sa + a_bytes, &tmB, &full_bar[stage], kb * kBlockK,
+          tma_load_2d_pair(sa, &tmA, &full_bar[stage], (seg == 1 ? k_pad : 0) + r * kBlockK,
+                           m_blk * 256 + static_cast<int>(crank) * kBlockM, kEvictNormal);
+          tma_load_2d_pair(sa + a_bytes, &tmB, &full_bar[stage], (seg == 2 ? k_pad : 0) + r * kBlockK,
                            n_blk * bn + static_cast<int>(crank) * (bn / 2), kEvictLast);
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
@@ -276,12 +287,12 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      for (int tile = pair; tile < num_tiles && !aborted(ab); tile += num_pairs) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1, ab);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * bn);
-        for (int kb = 0; kb < num_k_blocks; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
+        for (int kb = 0; kb < nkt; ++kb) {
+          mbar_wait(&full_bar[stage], phase, ab);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
           const uint64_t da = umma_desc_sw128(sa);
@@ -302,7 +313,7 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
       int m_blk, n_blk;
       decode(tile, m_blk, n_blk);
-      mbar_wait(&tfull_bar[acc], acc_phase);
+      mbar_wait(&tfull_bar[acc], acc_phase, ab);
       tc_fence_after();
       const int row = m_blk * 256 + static_cast<int>(crank) * kBlockM + q * 32 + lane;
       const bool row_ok = row < m_store;
@@ -359,7 +370,7 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 }  // namespace
 
 size_t gemm_smem_bytes(int bn, int stages) {
-  return 1024 + static_cast<size_t>(stages) * (kBlockM * kBlockK * 2 + bn * kBlockK * 2) + (2 * stages + 4) * 8 + 16;
+  return 1024 + static_cast<size_t>(stages) * (kBlockM * kBlockK * 2 + bn * kBlockK * 2) + (2 * stages + 4) * 8 + 32;
 }
 
 // Launch.  a: [m_pad rows, k_pad] bf16 (m_pad % 128 == 0, k_pad % 64 == 0); b: [n_pad rows, k_pad] bf16 with
@@ -369,9 +380,12 @@ cudaError_t launch_gemm_bf16(const GemmArgs& g, cudaStream_t stream) {
       g.n_store % 16)
     return cudaErrorInvalidValue;
   CUtensorMap tmA, tmB;
-  cudaError_t e = make_tmap_bf16_2d(&tmA, g.a, g.k_pad, g.m_pad, g.lda, kBlockK, kBlockM);
+  const int segs = g.segs == 3 ? 3 : 1;
+  const uint64_t k_inner = static_cast<uint64_t>(segs == 3 ? 2 : 1) * g.k_pad;  // split-bf16 operands are [hi | lo]
+  const long long spin_limit = g.spin_limit > 0 ? g.spin_limit : kSpinLimitDefault;
+  cudaError_t e = make_tmap_bf16_2d(&tmA, g.a, k_inner, g.m_pad, g.lda, kBlockK, kBlockM);
   if (e != cudaSuccess) return e;
-  e = make_tmap_bf16_2d(&tmB, g.b, g.k_pad, g.n_pad, g.ldb, kBlockK, g.bn);
+  e = make_tmap_bf16_2d(&tmB, g.b, k_inner, g.n_pad, g.ldb, kBlockK, g.bn);
   if (e != cudaSuccess) return e;
 
   static int use_pair = -1;
@@ -383,11 +397,11 @@ cudaError_t launch_gemm_bf16(const GemmArgs& g, cudaStream_t stream) {
   if (use_pair && g.m_pad % 256 == 0 && g.bn % 16 == 0 && (g.m_pad / 256) * (g.n_pad / g.bn) >= sms0 / 2) {
     // CTA-pair path: M = 256 tiles
     CUtensorMap tmBh;
-    e = make_tmap_bf16_2d(&tmBh, g.b, g.k_pad, g.n_pad, g.ldb, kBlockK, g.bn / 2);
+    e = make_tmap_bf16_2d(&tmBh, g.b, k_inner, g.n_pad, g.ldb, kBlockK, g.bn / 2);
     if (e != cudaSuccess) return e;
     int stages = 8;
     auto pair_smem = [&](int st) {
-      return 1024 + static_cast<size_t>(st) * (kBlockM * kBlockK * 2 + (g.bn / 2) * kBlockK * 2) + (2 * st + 4) * 8 + 16;
+      return 1024 + static_cast<size_t>(st) * (kBlockM * kBlockK * 2 + (g.bn / 2) * kBlockK * 2) + (2 * st + 4) * 8 + 32;
     };
     while (stages > 2 && pair_smem(stages) > 227 * 1024) --stages;
     const size_t smem = pair_smem(stages);
@@ -404,7 +418,7 @@ cudaError_t launch_gemm_bf16(const GemmArgs& g, cudaStream_t stream) {
     if (e != cudaSuccess) return e;                                                                               \
     kfn<<<grid, kGemmThreads, smem, stream>>>(tmA, tmBh, reinterpret_cast<OUT*>(g.d), g.bias, g.m_store,          \
                                               g.n_store, g.ldd, num_m_blocks, num_n_blocks, num_k_blocks, g.bn,   \
-                                              stages, panel);                                                     \
+                                              stages, panel, segs, g.k_pad, g.abort_flag, spin_limit);            \
   } while (0)
     if (g.out_bf16) {
       if (g.act == 0) IE_LAUNCH_PAIR(__nv_bfloat16, 0);
@@ -437,7 +451,8 @@ cudaError_t launch_gemm_bf16(const GemmArgs& g, cudaStream_t stream) {
     e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));            \
     if (e != cudaSuccess) return e;                                                                                \
     kfn<<<grid, kGemmThreads, smem, stream>>>(tmA, tmB, reinterpret_cast<OUT*>(g.d), g.bias, g.m_store, g.n_store, \
-                                              g.ldd, num_m_blocks, num_n_blocks, num_k_blocks, g.bn, stages, panel); \
+                                              g.ldd, num_m_blocks, num_n_blocks, num_k_blocks, g.bn, stages, panel,  \
+                                              segs, g.k_pad, g.abort_flag, spin_limit);                            \
   } while (0)
 
   if (g.out_bf16) {

@@ -1,0 +1,124 @@
+// Arithmetic shared by the recurrent kernels (lstm_layer.cu = the persistent kernel, lstm.cu = the per-timestep
+// fallback): the LSTM cell update on one 16-column accumulator chunk and the masked concat-pool accumulation.  Both
+// kernels call exactly these functions with the same association of operations, so every path gives the same bits.
+//
+// Reference arithmetic: torch nn.LSTM as wrapped by fastai's AWD_LSTM, called at
+// Issue_Embeddings/flask_app/inference.py:57,68 (gate rows i|f|g|o, c_t = f*c_{t-1} + i*g, h_t = o*tanh(c_t));
+// pooling: inference.py:239 ([mean | max | last] over the first len_i steps).
+#pragma once
+#include "ptx.cuh"
+
+namespace ie {
+
+// gate precision levels (LstmLayerArgs::gate_mode / LstmStepArgs::gate_mode)
+constexpr int kGatesFast = 2;   // tanh.approx.f32 (1 MUFU per transcendental, rel err 2^-11): the bf16 default
+constexpr int kGatesExp = 1;    // ex2.approx + rcp.approx (abs err ~1e-7): IE_CFG_ACCURATE_GATES
+constexpr int kGatesIeee = 0;   // expf + IEEE division: the fp32-accurate mode (IE_CFG_FP32)
+
+__device__ __forceinline__ float sigmoid_ieee(float x) { return 1.0f / (1.0f + expf(-x)); }
+__device__ __forceinline__ float tanh_ieee(float x) {
+  // 1 - 2/(e^{2x}+1) loses relative accuracy near 0: use expm1 there; odd in x
+  const float ax = fabsf(x);
+  float t;
+  if (ax < 0.55f) {
+    const float e = expm1f(2.0f * ax);
+    t = e / (e + 2.0f);
+  } else {
+    t = 1.0f - 2.0f / (expf(2.0f * ax) + 1.0f);
+  }
+  return copysignf(t, x);
+}
+
+// One accumulator chunk: 16 TMEM columns = 4 hidden units x (i, f, g, o) of one batch row.
+//   acc : the h_{t-1} W_hh^T part (f32 bits from tcgen05.ld)       gx : x_t W_ih^T + b_ih + b_hh (4 units x 4 gates)
+__device__ __forceinline__ void lstm_cell4(const uint32_t (&acc)[16], const float4 (&gx)[4], const float (&cprev)[4],
+                                           float (&cnew)[4], float (&hn)[4], int gate_mode) {
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const float zi = __uint_as_float(acc[4 * u + 0]) + gx[u].x;
+    const float zf = __uint_as_float(acc[4 * u + 1]) + gx[u].y;
+    const float zg = __uint_as_float(acc[4 * u + 2]) + gx[u].z;
+    const float zo = __uint_as_float(acc[4 * u + 3]) + gx[u].w;
+    if (gate_mode == kGatesFast) {
+      cnew[u] = sigmoid_fast(zf) * cprev[u] + sigmoid_fast(zi) * tanh_fast(zg);
+      hn[u] = sigmoid_fast(zo) * tanh_fast(cnew[u]);
+    } else if (gate_mode == kGatesExp) {
+      cnew[u] = sigmoid_acc(zf) * cprev[u] + sigmoid_acc(zi) * tanh_acc(zg);
+      hn[u] = sigmoid_acc(zo) * tanh_acc(cnew[u]);
+    } else {
+      cnew[u] = sigmoid_ieee(zf) * cprev[u] + sigmoid_ieee(zi) * tanh_ieee(zg);
+      hn[u] = sigmoid_ieee(zo) * tanh_ieee(cnew[u]);
+    }
+  }
+}
+
+// bf16 x 16 (one 256-bit load) -> the 4 x float4 Gx operands of a chunk
+__device__ __forceinline__ void gx_unpack_bf16(const uint32_t (&p)[8], float4 (&gx)[4]) {
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    gx[u].x = __uint_as_float(p[2 * u] << 16);
+    gx[u].y = __uint_as_float(p[2 * u] & 0xFFFF0000u);
+    gx[u].z = __uint_as_float(p[2 * u + 1] << 16);
+    gx[u].w = __uint_as_float(p[2 * u + 1] & 0xFFFF0000u);
+  }
+}
+
+// ---- masked concat-pool accumulators in global memory ------------------------------------------------------------
+// pool_sum : f32, sequential sum over t (one add per timestep, in timestep order)
+// pool_max : f32 encoded as an order-preserving u32 (enc_max / dec_max) so that the running max is a fire-and-forget
+//            red.max.u32
+// pool_last: f32, h at t == len-1
+// At t == 0 the accumulators are initialised with plain stores; for t > 0 the updates are reductions performed by the
+// L2 (no load, no latency on the step's critical path, no accumulator registers).  The (step, batch) counter
+// protocol of the persistent kernel orders step t's reductions after step t-1's (gpu-scope fence before the counter
+// increment), so the f32 sum is the same sequential sum a register accumulator would give: identical bits on every path.
+__device__ __forceinline__ uint32_t enc_max(float x) {
+  const uint32_t b = __float_as_uint(x);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float dec_max(uint32_t e) {
+  const uint32_t b = (e & 0x80000000u) ? (e & 0x7FFFFFFFu) : ~e;
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(b);
+#else
+  float f;
+  memcpy(&f, &b, 4);
+  return f;
+#endif
+}
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void red_max_u32(uint32_t* p, uint32_t v) {
+  asm volatile("red.relaxed.gpu.global.max.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// po: offset of the 4 units in the [row, out_pad] accumulator arrays; tg: global timestep; len: valid length of the row
+__device__ __forceinline__ void pool_accumulate4(float* pool_sum, float* pool_max, float* pool_last, long long po,
+                                                 const float (&hn)[4], int tg, int len) {
+  if (tg >= len) return;
+  uint32_t* pm = reinterpret_cast<uint32_t*>(pool_max) + po;
+  if (tg == 0) {
+    __stcg(reinterpret_cast<float4*>(pool_sum + po), make_float4(hn[0], hn[1], hn[2], hn[3]));
+    __stcg(reinterpret_cast<uint4*>(pm), make_uint4(enc_max(hn[0]), enc_max(hn[1]), enc_max(hn[2]), enc_max(hn[3])));
+  } else {
+    red_add_v4(pool_sum + po, hn[0], hn[1], hn[2], hn[3]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) red_max_u32(pm + u, enc_max(hn[u]));
+  }
+  if (tg == len - 1) __stcg(reinterpret_cast<float4*>(pool_last + po), make_float4(hn[0], hn[1], hn[2], hn[3]));
+}
+
+// h_t in the ring: bf16 (hi); with `lo_off` > 0 also the bf16 residual h - hi at column offset lo_off (the split-bf16
+// fp32-accurate mode: h ~ hi + lo to ~16 mantissa bits)
+__device__ __forceinline__ void store_h4(__nv_bfloat16* yp, const float (&hn)[4], long long lo_off) {
+  const __nv_bfloat162 a = __floats2bfloat162_rn(hn[0], hn[1]);
+  const __nv_bfloat162 b = __floats2bfloat162_rn(hn[2], hn[3]);
+  *reinterpret_cast<uint2*>(yp) = make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+  if (lo_off > 0) {
+    const float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+    *reinterpret_cast<uint2*>(yp + lo_off) =
+        make_uint2(pack_bf16x2(hn[0] - fa.x, hn[1] - fa.y), pack_bf16x2(hn[2] - fb.x, hn[3] - fb.y));
+  }
+}
+
+}  // namespace ie

@@ -1,0 +1,453 @@
+// THE persistent recurrent kernel: all timesteps of one LSTM layer (or of one time chunk of it) for up to kMaxBatches
+// independent batches of 256 rows in one launch.  Reference call sites of the arithmetic:
+// Issue_Embeddings/flask_app/inference.py:56-57, :66-68 (reset + forward), pooling :239.
+//
+//     z_t = Gx[t] + h_{t-1} W_hh^T ; i,f,o = sigmoid ; g = tanh ; c_t = f c_{t-1} + i g ; h_t = o tanh(c_t)
+//
+// Work decomposition ("rotating schedule", round-1 experiment lstm_rot.cu, now the only persistent kernel -- it
+// replaced the static deals of lstm_seq.cu / lstm_wide.cu, which left 23 % of the CTA pairs idle at H = 2400):
+//   * a CTA pair (cluster of 2 on one TPC, tcgen05 cta_group::2) is one M = 256 tensor core: CTA r holds batch rows
+//     [128 r, +128) of the h tile and half of the W_hh tile; an accumulator tile is 256 rows x 256 columns = 64 hidden
+//     units x (i,f,g,o) -- weight rows are pre-permuted to [tile][cta][unit][gate] so a thread finds the four gates of a
+//     unit in adjacent TMEM columns and the cell update needs no cross-thread traffic;
+//   * the work ITEMS  n = t * C + g * tiles + j  (C = ng * tiles; timestep t, batch g, column tile j) are dealt round-robin
+//     in that global order over the P resident pairs: pair p runs items p, p + P, p + 2P, ...  Item n needs h_{t-1} of
+//     batch g, i.e. items n - C - j .. n - C + (tiles - 1 - j), all with smaller indices; every pair walks its items in
+//     increasing order, so the item with the globally smallest index can always run: no wait cycle for any P, C, T.
+//     With C >= 2P + tiles (five batches at H = 2400: 190 >= 148 + 38) an item's inputs were finished two rounds
+//     earlier and every pair issues MMAs back to back;
+//   * per item: K/64 k-blocks of h (TMA, 128B swizzle, 3-stage ring) and W_hh (own ring, free-running: weights do not
+//     depend on the step) -> 4 x tcgen05.mma per k-block into one of two TMEM accumulator slots -> 16 epilogue warps
+//     (tcgen05.ld, + Gx, gates, c_t, h_t as bf16 into slot t+1 of the hidden-state ring = next step's A operand and the
+//     next layer's GEMM input) -> gpu-scope fence + red.add on the (step, batch) counter;
+//   * the cell state moves between SMs from step to step: it lives in global memory (L2) and is read with ld.global.cg
+//     after the pair has seen the (t-1, g) counter; the pooling accumulators of the last layer are L2 reductions
+//     (lstm_common.cuh), so neither sits on the step's critical path;
+//   * split-bf16 ("fp32-accurate") mode: segs = 3 runs the K loop over [h_hi | h_lo | h_hi] x [W_hi | W_hi | W_lo]
+//     (hi = bf16(x), lo = bf16(x - hi); the dropped lo*lo term is 2^-18 relative) -- same kernel, three times the MMAs.
+//
+// All CTAs must be co-resident: the launch is cooperative (cudaLaunchAttributeCooperative), so it either gets the
+// whole grid resident or fails; a wait that still exceeds its limit raises the abort protocol of ptx.cuh (no trap).
+#include <cmath>
+
+#include "kernels.h"
+#include "lstm_common.cuh"
+#include "ptx.cuh"
+
+namespace ie {
+
+namespace {
+
+constexpr int kLThreads = 640;          // 4 role warps + 16 epilogue warps (4 per TMEM lane quarter, 64 columns each)
+constexpr int kLGA = 2, kLAStages = 3;  // h ring: 3 stages x 2 k-blocks x 16 KB
+constexpr int kLGW = 2, kLWStages = 3;  // W ring: 3 stages x 2 k-blocks x 16 KB
+constexpr int kLTileN = 256;            // accumulator columns per tile = 64 hidden units
+constexpr int kLHalfRows = 128;         // W rows each CTA of the pair contributes
+
+__device__ __forceinline__ void st_release_cta(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_cta(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+  return v;
+}
+// bounded, backed-off spin of one lane until the shared sequence number reaches `target`
+__device__ __forceinline__ void wait_seq_ge(const uint32_t* p, uint32_t target, const Abort& ab) {
+  if (ld_acquire_cta(p) >= target) return;
+  if (aborted(ab)) return;
+  const long long t0 = clock64();
+  uint32_t spins = 0;
+  while (ld_acquire_cta(p) < target) {
+    __nanosleep(64);
+    if (((++spins) & 0x3Fu) == 0 && abort_poll(ab, t0)) return;
+  }
+}
+
+struct KArgs {
+  const void* gx;        // f32 or bf16 [rows, 4*out_pad]; row = t_local*b_pad + brow, or the token id (TOK)
+  const int* tok;        // TOK: time-major token ids of the whole call, index (t0 + t)*b_pad + brow
+  float* cstate;         // [b_pad, out_pad]
+  __nv_bfloat16* y;      // ring [(T+1)*b_pad, ldy] of this time chunk: slot 0 = h before the chunk, slot t+1 = h_t
+  float* raw;            // optional [b_pad, T_total, raw_ld]
+  float* pool_sum;       // optional (last layer)
+  float* pool_max;
+  float* pool_last;
+  const int* lengths;
+  unsigned* step_done;   // [T*ng] zero-initialised (chunk-local)
+  unsigned* abort_flag;
+  long long spin_limit;
+  long long ldy, raw_ld;
+  long long* trace;
+  long long* diag;
+  int T, t0, T_total, ng, tiles, out_pad, nkb, segs, kh_pad, gate_mode, trace_items, fault;
+};
+
+// TOK: Gx rows are rows of the per-token input-projection table; GXBF: Gx / table stored as bf16
+template <bool TOK, bool GXBF>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kLThreads, 1)
+lstm_layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ CUtensorMap tm_w,
+                  const __grid_constant__ KArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t rawaddr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (rawaddr & 1023u)) & 1023u);
+
+  constexpr uint32_t a_bytes = 128 * 64 * 2;
+  constexpr uint32_t w_bytes = kLHalfRows * 64 * 2;
+  uint8_t* a_ring = smem;
+  uint8_t* w_ring = smem + kLAStages * kLGA * a_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(w_ring + kLWStages * kLGW * w_bytes);
+  uint64_t* afull = bars;                   // [kLAStages] leader's copy is live
+  uint64_t* aempty = afull + kLAStages;
+  uint64_t* wfull = aempty + kLAStages;     // [kLWStages]
+  uint64_t* wempty = wfull + kLWStages;
+  uint64_t* tfull = wempty + kLWStages;     // [2] accumulator slot holds a finished item (both CTAs' copies live)
+  uint64_t* tempty = tfull + 2;             // [2] accumulator slot drained by both CTAs (leader's copy is live)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint32_t* cready = tmem_slot + 1;         // number of this CTA's items whose (t-1, g) counter the watcher has seen
+  uint32_t* abort_s = tmem_slot + 2;
+  const Abort ab{abort_s, a.abort_flag, a.spin_limit};
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  long long* const trace = a.trace;
+  // optional timeline of the pair's first `trace_items` items: [cta][k][12] (%globaltimer ns; slots 8-11 SM cycles)
+#define IE_TRACE(slot, kk) do { if (trace && (kk) < a.trace_items) { unsigned long long _g; \
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_g)); \
+    trace[(static_cast<long long>(blockIdx.x) * a.trace_items + (kk)) * 12 + (slot)] = static_cast<long long>(_g); } } while (0)
+#define IE_TRACE_VAL(slot, kk, v) do { if (trace && (kk) < a.trace_items) \
+    trace[(static_cast<long long>(blockIdx.x) * a.trace_items + (kk)) * 12 + (slot)] = (v); } while (0)
+  const uint32_t crank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1;
+  const int P = static_cast<int>(gridDim.x >> 1);
+  const int tiles = a.tiles, ng = a.ng;
+  const int C = ng * tiles;
+  const long long total = static_cast<long long>(a.T) * C;
+  const int b_pad = 256 * ng;
+  const unsigned batch_ctas = 2u * static_cast<unsigned>(tiles);  // CTAs that publish a (step, batch)
+  const int nkt = a.nkb * a.segs;                                   // k-blocks per item
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_h);
+    tma_prefetch_desc(&tm_w);
+    if (a.diag != nullptr && blockIdx.x == 0) {  // SM clock of this launch = d(clock64) / d(globaltimer)
+      unsigned long long g;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+      a.diag[0] = clock64();
+      a.diag[1] = static_cast<long long>(g);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kLAStages; ++s) {
+      mbar_init(&afull[s], 2);
+      mbar_init(&aempty[s], 1);
+    }
+    for (int s = 0; s < kLWStages; ++s) {
+      mbar_init(&wfull[s], 2);
+      mbar_init(&wempty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull[s], 1);
+      mbar_init(&tempty[s], 2);
+    }
+    *cready = 0;
+    *abort_s = 0;
+    fence_barrier_init();
+  }
+  cluster_sync();
+  if (warp == 2) tmem_alloc_pair(tmem_slot, 512);
+  tc_fence_before();
+  cluster_sync();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ---------------- h producer ------------------------------------------------------------------------------
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int k = 0;
+      for (long long n = pair; n < total && !aborted(ab); n += P, ++k) {
+        const int t = static_cast<int>(n / C);
+        const int g = static_cast<int>(n - static_cast<long long>(t) * C) / tiles;
+        wait_seq_ge(cready, static_cast<uint32_t>(k + 1), ab);  // the watcher (warp 2) has seen counter (t-1, g)
+        if (t > 0) fence_proxy_async();  // h_{t-1} was written through the generic proxy, TMA reads it
+        IE_TRACE(0, k);
+        const int row0 = t * b_pad + g * 256 + static_cast<int>(crank) * 128;  // ring slot t = h_{t-1} (chunk-local)
+        for (int kb0 = 0; kb0 < nkt; kb0 += kLGA) {
+          const int nb = min(kLGA, nkt - kb0);
+          mbar_wait(&aempty[stage], phase ^ 1, ab);
+          if (crank == 0) mbar_arrive_expect_tx(&afull[stage], 2 * nb * a_bytes);
+          else mbar_arrive_remote(&afull[stage], 0);
+          for (int q = 0; q < nb; ++q) {
+            const int kb = kb0 + q;
+            const int seg = kb / a.nkb, r = kb - seg * a.nkb;          // split-bf16: [h_hi | h_lo | h_hi]
+            tma_load_2d_pair(a_ring + (stage * kLGA + q) * a_bytes, &tm_h, &afull[stage],
+                             (seg == 1 ? a.kh_pad : 0) + r * 64, row0, kEvictNormal);
+          }
+          if (++stage == kLAStages) { stage = 0; phase ^= 1; }
+        }
+        IE_TRACE(1, k);
+      }
+    }
+  } else if (warp == 2) {
+    // ---------------- counter watcher: runs ahead of the h producer and the epilogue ----------------------------
+    // The counter load and the gpu-scope fence after it cost ~1-2 us next to the TMA streams; done here they are off
+    // the h producer's path.
+    if (lane == 0) {
+      int k = 0;
+      for (long long n = pair; n < total && !aborted(ab); n += P, ++k) {
+        const int t = static_cast<int>(n / C);
+        const int g = static_cast<int>(n - static_cast<long long>(t) * C) / tiles;
+        if (t > 0) wait_flag_ge_relaxed(a.step_done + (t - 1) * ng + g, batch_ctas, ab);  // ends with a gpu-scope fence
+        st_release_cta(cready, static_cast<uint32_t>(k + 1));
+      }
+    }
+  } else if (warp == 3) {
+    // ---------------- W producer: free-running ahead of h ----------------------------------------------------
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long n = pair; n < total && !aborted(ab); n += P) {
+        const int j = static_cast<int>(n % C) % tiles;
+        const int wrow0 = (2 * j + static_cast<int>(crank)) * kLHalfRows;  // slices are [cta][unit][gate], 128 rows each
+        for (int kb0 = 0; kb0 < nkt; kb0 += kLGW) {
+          const int nb = min(kLGW, nkt - kb0);
+          mbar_wait(&wempty[stage], phase ^ 1, ab);
+          if (crank == 0) mbar_arrive_expect_tx(&wfull[stage], 2 * nb * w_bytes);
+          else mbar_arrive_remote(&wfull[stage], 0);
+          for (int q = 0; q < nb; ++q) {
+            const int kb = kb0 + q;
+            const int seg = kb / a.nkb, r = kb - seg * a.nkb;          // split-bf16: [W_hi | W_hi | W_lo]
+            tma_load_2d_pair(w_ring + (stage * kLGW + q) * w_bytes, &tm_w, &wfull[stage],
+                             (seg == 2 ? a.kh_pad : 0) + r * 64, wrow0, kEvictLast);
+          }
+          if (++stage == kLWStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- UMMA issuer (leader CTA) --------------------------------------------------------------
+    if (crank == 0 && lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(256, kLTileN);
+      const uint32_t a_base = smem_u32(a_ring);
+      const uint32_t w_base = smem_u32(w_ring);
+      int as = 0, ws = 0;
+      uint32_t aph = 0, wph = 0;
+      int k = 0;
+      for (long long n = pair; n < total && !aborted(ab); n += P, ++k) {
+        const int slot = k & 1;
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(slot * kLTileN);
+        long long wa = 0, ww = 0, t_first = 0;
+        if (k >= 2) {  // the slot's previous item (k - 2) must have been read out of TMEM by both CTAs
+          const long long c0 = trace ? clock64() : 0;
+          mbar_wait(&tempty[slot], static_cast<uint32_t>(((k >> 1) - 1) & 1), ab);
+          IE_TRACE_VAL(11, k, trace ? clock64() - c0 : 0);
+        }
+        for (int kb = 0; kb < nkt; ++kb) {
+          const int ja = kb % kLGA, jw = kb % kLGW;
+          if (ja == 0) {
+            const long long c0 = trace ? clock64() : 0;
+            mbar_wait(&afull[as], aph, ab);
+            if (kb == 0) { IE_TRACE(2, k); t_first = trace ? clock64() : 0; }
+            else if (trace) wa += clock64() - c0;
+          }
+          if (jw == 0) {
+            const long long c0 = trace ? clock64() : 0;
+            mbar_wait(&wfull[ws], wph, ab);
+            if (trace) ww += clock64() - c0;
+          }
+          tc_fence_after();
+          const uint64_t da = umma_desc_sw128(a_base + (as * kLGA + ja) * a_bytes);
+          const uint64_t db = umma_desc_sw128(w_base + (ws * kLGW + jw) * w_bytes);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) umma_bf16_pair(tmem_d, da + 2 * q, db + 2 * q, idesc, (kb | q) != 0);
+          const bool last = (kb == nkt - 1);
+          if (ja == kLGA - 1 || last) {
+            umma_commit_pair_mc(&aempty[as], 0x3);
+            if (++as == kLAStages) { as = 0; aph ^= 1; }
+          }
+          if (jw == kLGW - 1 || last) {
+            umma_commit_pair_mc(&wempty[ws], 0x3);
+            if (++ws == kLWStages) { ws = 0; wph ^= 1; }
+          }
+        }
+        umma_commit_pair_mc(&tfull[slot], 0x3);
+        IE_TRACE(3, k);
+        IE_TRACE_VAL(8, k, wa);
+        IE_TRACE_VAL(9, k, ww);
+        IE_TRACE_VAL(10, k, trace ? clock64() - t_first : 0);
+      }
+    }
+  } else if (warp >= 4) {
+    // ---------------- epilogue (never leaves its loop early: named barriers inside; in drain mode its waits return
+    //                  at once and it runs through the remaining items) -----------------------------------------------
+    const int e = warp - 4;
+    const int q = e & 3;
+    const int cq = e >> 2;  // which 64 of the tile's 256 columns (4 chunks of 16 = 16 hidden units per thread)
+    const int row = static_cast<int>(crank) * 128 + q * 32 + lane;
+    const bool pooled = a.pool_sum != nullptr;
+    const long long lo_off = a.segs > 1 ? a.kh_pad : 0;
+    int k = 0;
+    for (long long n = pair; n < total; n += P, ++k) {
+      const int t = static_cast<int>(n / C);
+      const int c = static_cast<int>(n - static_cast<long long>(t) * C);
+      const int g = c / tiles, j = c % tiles;
+      const int tg = a.t0 + t;  // global timestep
+      const int slot = k & 1;
+      const int brow = g * 256 + row;
+      const int unit0 = j * 64 + cq * 16;
+      const int len = pooled ? a.lengths[brow] : 1;
+      const long long grow = TOK ? static_cast<long long>(__ldg(a.tok + static_cast<long long>(tg) * b_pad + brow))
+                                 : static_cast<long long>(t) * b_pad + brow;  // TOK: per-token projection table
+      float* cp = a.cstate + static_cast<long long>(brow) * a.out_pad + unit0;
+      __nv_bfloat16* yrow = a.y + (static_cast<long long>(t + 1) * b_pad + brow) * a.ldy + unit0;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(slot * kLTileN + cq * 64);
+      // all of this thread's Gx (4 chunks x 4 units x 4 gates) and c are loaded while the MMAs still run
+      constexpr int kCh = 4;
+      constexpr int kGW = GXBF ? 8 : 16;   // 32-bit words of Gx per chunk
+      uint32_t gxw[kCh][kGW];
+      float4 cr[kCh];
+      if constexpr (GXBF) {
+        const __nv_bfloat16* gxp = reinterpret_cast<const __nv_bfloat16*>(a.gx) + grow * (4ll * a.out_pad) + 4ll * unit0;
+#pragma unroll
+        for (int ch = 0; ch < kCh; ++ch) ldg_stream8_b32(gxp + ch * 16, &gxw[ch][0]);
+      } else {
+        const float* gxp = reinterpret_cast<const float*>(a.gx) + grow * (4ll * a.out_pad) + 4ll * unit0;
+#pragma unroll
+        for (int ch = 0; ch < kCh; ++ch) {
+          ldg_stream8_b32(gxp + ch * 16, &gxw[ch][0]);
+          ldg_stream8_b32(gxp + ch * 16 + 8, &gxw[ch][kGW - 8]);
+        }
+      }
+      // c_{t-1} of this chain was written by another pair: read it (from L2) only after (t-1, g) has been seen here
+      if (lane == 0) wait_seq_ge(cready, static_cast<uint32_t>(k + 1), ab);
+      __syncwarp();
+#pragma unroll
+      for (int ch = 0; ch < kCh; ++ch)
+        cr[ch] = (tg == 0) ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldcg(reinterpret_cast<const float4*>(cp) + ch);
+      if (threadIdx.x == 128) IE_TRACE(7, k);
+      mbar_wait(&tfull[slot], static_cast<uint32_t>((k >> 1) & 1), ab);
+      tc_fence_after();
+      if (threadIdx.x == 128) IE_TRACE(4, k);
+#pragma unroll
+      for (int ch = 0; ch < kCh; ++ch) {
+        uint32_t r[16];
+        __syncwarp();
+        tmem_ld16(taddr + ch * 16, r);
+        tmem_ld_wait();
+        float4 gx4[4];
+        if constexpr (GXBF) {
+          gx_unpack_bf16(gxw[ch], gx4);
+        } else {
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            gx4[u] = make_float4(__uint_as_float(gxw[ch][4 * u]), __uint_as_float(gxw[ch][4 * u + 1]),
+                                 __uint_as_float(gxw[ch][4 * u + 2]), __uint_as_float(gxw[ch][4 * u + 3]));
+        }
+        const float cprev[4] = {cr[ch].x, cr[ch].y, cr[ch].z, cr[ch].w};
+        float cnew[4], hn[4];
+        lstm_cell4(r, gx4, cprev, cnew, hn, a.gate_mode);
+        __stcg(reinterpret_cast<float4*>(cp) + ch, make_float4(cnew[0], cnew[1], cnew[2], cnew[3]));
+        store_h4(yrow + ch * 4, hn, lo_off);
+        if (a.raw != nullptr) {
+          float4* rp = reinterpret_cast<float4*>(a.raw + (static_cast<long long>(brow) * a.T_total + tg) * a.raw_ld + unit0 + ch * 4);
+          *rp = make_float4(hn[0], hn[1], hn[2], hn[3]);
+        }
+        if (pooled)
+          pool_accumulate4(a.pool_sum, a.pool_max, a.pool_last, static_cast<long long>(brow) * a.out_pad + unit0 + ch * 4, hn,
+                           tg, len);
+      }
+      // publish (step t, batch g): accumulator slot drained, h_t / c_t / pooling state visible
+      if (threadIdx.x == 128) IE_TRACE(5, k);
+      tc_fence_before();
+      named_bar_sync(1, 512);
+      if (threadIdx.x == 128) {
+        mbar_arrive_remote(&tempty[slot], 0);
+        __threadfence();
+        // fault injection for the abort-protocol test (IE_DEBUG_FAULT): item (t=1, g=0, j=0) is never published
+        if (!(a.fault && n == C)) red_relaxed_add(a.step_done + t * ng + g, 1u);
+        IE_TRACE(6, k);
+      }
+    }
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  cluster_sync();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, 512);
+  }
+  if (a.diag != nullptr && threadIdx.x == 0 && blockIdx.x == 0) {
+    unsigned long long g;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+    a.diag[2] = clock64();
+    a.diag[3] = static_cast<long long>(g);
+  }
+#undef IE_TRACE
+#undef IE_TRACE_VAL
+}
+
+size_t layer_smem_bytes() {
+  return 1024 + static_cast<size_t>(kLAStages) * kLGA * 128 * 64 * 2 + static_cast<size_t>(kLWStages) * kLGW * kLHalfRows * 64 * 2 +
+         (2 * kLAStages + 2 * kLWStages + 4) * 8 + 32;
+}
+
+template <bool TOK, bool GXBF>
+cudaError_t launch_layer_t(const LstmLayerArgs& a, int pairs, int tiles, cudaStream_t stream) {
+  auto kfn = lstm_layer_kernel<TOK, GXBF>;
+  const size_t smem = layer_smem_bytes();
+  // function attributes are per device: set on every launch (cheap), never cached in a process-wide flag
+  cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (e != cudaSuccess) return e;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * (a.check_only ? a.num_sms / 2 : pairs));
+  cfg.blockDim = dim3(kLThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  if (a.check_only) {
+    int max_clusters = 0;
+    e = cudaOccupancyMaxActiveClusters(&max_clusters, kfn, &cfg);
+    if (e != cudaSuccess) return e;
+    return max_clusters >= a.num_sms / 2 ? cudaSuccess : cudaErrorCooperativeLaunchTooLarge;
+  }
+  KArgs k{};
+  k.gx = a.gx; k.tok = a.tok; k.cstate = a.c; k.y = a.y; k.raw = a.raw;
+  k.pool_sum = a.pool_sum; k.pool_max = a.pool_max; k.pool_last = a.pool_last; k.lengths = a.lengths;
+  k.step_done = a.step_done; k.abort_flag = a.abort_flag;
+  k.spin_limit = a.spin_limit > 0 ? a.spin_limit : kSpinLimitDefault;
+  k.ldy = a.ldy; k.raw_ld = a.raw_ld; k.trace = a.trace; k.diag = a.diag;
+  k.T = a.T; k.t0 = a.t0; k.T_total = a.T_total; k.ng = a.ng; k.tiles = tiles; k.out_pad = a.out_pad;
+  k.nkb = a.kh_pad / 64; k.segs = a.segs; k.kh_pad = a.kh_pad; k.gate_mode = a.gate_mode;
+  k.trace_items = a.trace_items; k.fault = a.fault;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = a.cooperative ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kfn, a.tm_h, a.tm_w, k);
+}
+
+}  // namespace
+
+int lstm_layer_pairs(const LstmLayerArgs& a) {
+  const long long total = static_cast<long long>(a.T) * a.ng * (a.n_cta / 2);
+  long long pairs = a.num_sms / 2;
+  if (pairs > total) pairs = total;
+  return static_cast<int>(pairs);
+}
+
+// a.check_only: only verify that a full grid can be co-resident.  Requires u == 32 per CTA (64 units per pair tile).
+cudaError_t launch_lstm_layer(const LstmLayerArgs& a, cudaStream_t stream) {
+  if (a.u != 32 || a.n_cta % 2 || a.kh_pad % 64 || a.ng < 1 || a.ng > kMaxBatches || a.T < 1 || (a.segs != 1 && a.segs != 3))
+    return cudaErrorInvalidValue;
+  const int tiles = a.n_cta / 2;
+  const int pairs = lstm_layer_pairs(a);
+  if (pairs < 1) return cudaErrorInvalidValue;
+  const bool tok = a.tok != nullptr;  // layer 0 reading its input projection from the per-token table
+  if (a.gx_bf16) return tok ? launch_layer_t<true, true>(a, pairs, tiles, stream) : launch_layer_t<false, true>(a, pairs, tiles, stream);
+  return tok ? launch_layer_t<true, false>(a, pairs, tiles, stream) : launch_layer_t<false, false>(a, pairs, tiles, stream);
+}
+
+}  // namespace ie

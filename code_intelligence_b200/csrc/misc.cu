@@ -1,6 +1,9 @@
 // Memory-bound helper kernels of the encoder path (HBM-bound byte movement: coalesced 128-bit accesses, no
 // tensor cores) and the TMA descriptor factory.
+#include <cstring>
+
 #include "kernels.h"
+#include "lstm_common.cuh"
 #include "ptx.cuh"
 
 namespace ie {
@@ -50,15 +53,16 @@ namespace {
 // Rows b >= B of the 128-padded batch get the pad token.
 // ---------------------------------------------------------------------------------------------
 __global__ void embed_gather_kernel(const int64_t* __restrict__ ids, int B, int T, int b_pad,
-                                    const uint4* __restrict__ emb, int vocab, int chunks /* e_pad*2/16 */,
-                                    uint4* __restrict__ x0, long long ldx_chunks, int pad_idx, int* err_flag) {
+                                    const uint4* __restrict__ emb, int vocab, int chunks /* row bytes / 16 */,
+                                    uint4* __restrict__ x0, long long ldx_chunks, int pad_idx, int* err_flag, int t0, int Tc) {
   const int warps_per_block = blockDim.x >> 5;
   const long long row = static_cast<long long>(blockIdx.x) * warps_per_block + (threadIdx.x >> 5);
-  const long long total = static_cast<long long>(T) * b_pad;
+  const long long total = static_cast<long long>(Tc) * b_pad;
   if (row >= total) return;
   const int lane = threadIdx.x & 31;
-  const int t = static_cast<int>(row / b_pad);
-  const int b = static_cast<int>(row - static_cast<long long>(t) * b_pad);
+  const int tl = static_cast<int>(row / b_pad);
+  const int b = static_cast<int>(row - static_cast<long long>(tl) * b_pad);
+  const int t = t0 + tl;
   long long id = pad_idx;
   if (b < B) id = ids[static_cast<long long>(b) * T + t];
   if (id < 0 || id >= vocab) {
@@ -97,46 +101,44 @@ __global__ void pool_finalize_kernel(const float* __restrict__ pool_sum, const f
   const float inv = 1.0f / static_cast<float>(lengths[b]);
   const long long po = static_cast<long long>(b) * out_pad;
   float* o = out + static_cast<long long>(b) * 3 * e;
+  const uint32_t* pmax = reinterpret_cast<const uint32_t*>(pool_max);  // order-preserving encoding (lstm_common.cuh)
   for (int i = threadIdx.x; i < e; i += blockDim.x) {
     o[i] = pool_sum[po + i] * inv;
-    o[e + i] = pool_max[po + i];
+    o[e + i] = dec_max(pmax[po + i]);
     o[2 * e + i] = pool_last[po + i];
   }
 }
 
-// Pooling from the last layer's f32 hidden states raw [b_pad, T, raw_ld] (written by the recurrent kernel): one thread per
-// (row, unit), t ascending -- the same sequential f32 sum, max and last as the in-kernel accumulators, so the same bits --
-// straight to out[b] = [sum/len | max | last].  (api.cu: IE_POOL_RAW)
-__global__ void pool_from_raw_kernel(const float* __restrict__ raw, const int* __restrict__ lengths, int T, int e,
-                                     long long raw_ld, float* __restrict__ out) {
-  const int b = blockIdx.x;
-  const int i = blockIdx.y * blockDim.x + threadIdx.x;
-  if (i >= e) return;
-  const int len = lengths[b];
-  const float* p = raw + static_cast<long long>(b) * T * raw_ld + i;
-  float s = p[0], m = s, last = s;
-  for (int t = 1; t < len; ++t) {
-    last = p[static_cast<long long>(t) * raw_ld];
-    s += last;
-    m = fmaxf(m, last);
+// device-pointer mode: the caller's lengths cannot be validated on the host -- clamp them to [1, T] here (a length of
+// 0 would give 1/0 and max = -inf in pool_finalize) and raise err_flag[2]; padded rows get length 1
+__global__ void prep_lengths_kernel(const int* __restrict__ in, int B, int T, int b_pad, int* __restrict__ out, int* err_flag) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= b_pad) return;
+  int v = 1;
+  if (i < B) {
+    v = in[i];
+    if (v < 1 || v > T) {
+      atomicExch(err_flag + 2, 1);
+      v = v < 1 ? 1 : T;
+    }
   }
-  float* o = out + static_cast<long long>(b) * 3 * e;
-  o[i] = s * (1.0f / static_cast<float>(len));
-  o[e + i] = m;
-  o[2 * e + i] = last;
+  out[i] = v;
 }
 
 __global__ void convert_rows_kernel(const float* __restrict__ src, long long ld_src, int cols, const int* __restrict__ perm,
-                                    int rows_dst, __nv_bfloat16* __restrict__ dst, long long ld_dst) {
+                                    int rows_dst, __nv_bfloat16* __restrict__ dst, long long ld_dst, int lo_off) {
   const int r = blockIdx.x;
   if (r >= rows_dst) return;
   const int sr = perm ? perm[r] : r;
   __nv_bfloat16* d = dst + static_cast<long long>(r) * ld_dst;
   const float* s = src + static_cast<long long>(sr < 0 ? 0 : sr) * ld_src;
-  for (int c = threadIdx.x; c < ld_dst; c += blockDim.x) {
+  const int width = lo_off > 0 ? lo_off : static_cast<int>(ld_dst);
+  for (int c = threadIdx.x; c < width; c += blockDim.x) {
     float v = 0.0f;
     if (sr >= 0 && c < cols) v = s[c];
-    d[c] = __float2bfloat16_rn(v);
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    d[c] = hi;
+    if (lo_off > 0) d[lo_off + c] = __float2bfloat16_rn(v - __bfloat162float(hi));
   }
 }
 
@@ -149,15 +151,15 @@ __global__ void fill_f32_kernel(float* p, size_t n, float v) {
 }  // namespace
 
 cudaError_t launch_embed_gather(const int64_t* ids, int B, int T, int b_pad, const __nv_bfloat16* emb, int vocab,
-                                int e_pad, __nv_bfloat16* x0, long long ldx, int pad_idx, int* err_flag,
+                                int e_pad, __nv_bfloat16* x0, long long ldx, int pad_idx, int* err_flag, int t0, int Tc,
                                 cudaStream_t stream) {
   if (e_pad % 8 || ldx % 8) return cudaErrorInvalidValue;
-  const long long rows = static_cast<long long>(T) * b_pad;
+  const long long rows = static_cast<long long>(Tc) * b_pad;
   const int wpb = 8;
   const long long blocks = (rows + wpb - 1) / wpb;
   embed_gather_kernel<<<static_cast<unsigned>(blocks), wpb * 32, 0, stream>>>(
       ids, B, T, b_pad, reinterpret_cast<const uint4*>(emb), vocab, e_pad / 8, reinterpret_cast<uint4*>(x0), ldx / 8,
-      pad_idx, err_flag);
+      pad_idx, err_flag, t0, Tc);
   return cudaGetLastError();
 }
 
@@ -175,16 +177,16 @@ cudaError_t launch_pool_finalize(const float* pool_sum, const float* pool_max, c
   return cudaGetLastError();
 }
 
-cudaError_t launch_pool_from_raw(const float* raw, const int* lengths, int B, int T, int e, long long raw_ld, float* out,
-                                 cudaStream_t stream) {
-  const dim3 grid(B, (e + 127) / 128);
-  pool_from_raw_kernel<<<grid, 128, 0, stream>>>(raw, lengths, T, e, raw_ld, out);
+cudaError_t launch_prep_lengths(const int* lengths_in, int B, int T, int b_pad, int* lengths_out, int* err_flag,
+                                cudaStream_t stream) {
+  prep_lengths_kernel<<<(b_pad + 255) / 256, 256, 0, stream>>>(lengths_in, B, T, b_pad, lengths_out, err_flag);
   return cudaGetLastError();
 }
 
 cudaError_t launch_convert_rows(const float* src, long long ld_src, int cols, const int* perm, int rows_dst,
-                                __nv_bfloat16* dst, long long ld_dst, cudaStream_t stream) {
-  convert_rows_kernel<<<rows_dst, 256, 0, stream>>>(src, ld_src, cols, perm, rows_dst, dst, ld_dst);
+                                __nv_bfloat16* dst, long long ld_dst, int lo_off, cudaStream_t stream) {
+  if (lo_off > 0 && ld_dst < 2ll * lo_off) return cudaErrorInvalidValue;
+  convert_rows_kernel<<<rows_dst, 256, 0, stream>>>(src, ld_src, cols, perm, rows_dst, dst, ld_dst, lo_off);
   return cudaGetLastError();
 }
 

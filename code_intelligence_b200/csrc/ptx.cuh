@@ -61,13 +61,50 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug becomes a trapped kernel (CUDA error) after ~2 s instead of a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+// ----------------------------------------------------------------------------------------------
+// Abort protocol of every spin in this directory.  A wait that exceeds `limit` SM cycles (a protocol bug, or a
+// persistent grid that lost co-residency) does NOT trap -- a trap poisons the CUDA context of every handle in the
+// process, and include/issue_emb_b200.h promises error codes.  Instead the waiter raises the CTA's shared-memory flag
+// and the launch's global flag (the handle's error word) and returns; from then on every wait of the CTA returns at
+// once ("drain mode": role loops fall through, results are garbage, the kernel terminates), other CTAs adopt the
+// global flag the next time one of their spins polls it, and the host turns the flag into IE_ERR_CUDA.
+// ----------------------------------------------------------------------------------------------
+struct Abort {
+  uint32_t* s;      // this CTA's flag in shared memory (initialised to 0 by the thread that initialises the barriers)
+  unsigned* g;      // the launch's flag in global memory (nullptr: none)
+  long long limit;  // SM cycles a single wait may take
+};
+constexpr long long kSpinLimitDefault = 4000000000ll;  // ~2 s
+
+__device__ __forceinline__ bool aborted(const Abort& a) {
+  uint32_t v;
+  asm volatile("ld.volatile.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(a.s)) : "memory");
+  return v != 0;
+}
+static __device__ __noinline__ void abort_raise(const Abort& a) {
+  asm volatile("st.volatile.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(a.s)), "r"(1u) : "memory");
+  if (a.g != nullptr) atomicExch(a.g, 1u);
+}
+// slow-path poll (every few hundred spins): true once this CTA is in drain mode
+static __device__ __noinline__ bool abort_poll(const Abort& a, long long t0) {
+  if (aborted(a)) return true;
+  bool hit = (clock64() - t0) > a.limit;
+  if (!hit && a.g != nullptr) {
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(a.g) : "memory");
+    hit = v != 0;
+  }
+  if (hit) abort_raise(a);
+  return hit;
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, const Abort& ab) {
   if (mbar_try_wait(bar, parity)) return;
+  if (aborted(ab)) return;
   const long long t0 = clock64();
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (((++spins) & 0x3FFu) == 0 && (clock64() - t0) > 4000000000ll) __trap();
+    if (((++spins) & 0xFFu) == 0 && abort_poll(ab, t0)) return;
   }
 }
 
@@ -250,13 +287,14 @@ __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-// bounded spin until *p >= target (trap instead of hanging the GPU on a protocol bug)
-__device__ __forceinline__ void wait_flag_ge(const unsigned* p, unsigned target) {
+// bounded spin until *p >= target (abort protocol above instead of hanging the GPU on a protocol bug)
+__device__ __forceinline__ void wait_flag_ge(const unsigned* p, unsigned target, const Abort& ab) {
   if (ld_acquire(p) >= target) return;
+  if (aborted(ab)) return;
   const long long t0 = clock64();
   uint32_t spins = 0;
   while (ld_acquire(p) < target) {
-    if (((++spins) & 0xFFu) == 0 && (clock64() - t0) > 4000000000ll) __trap();
+    if (((++spins) & 0x3Fu) == 0 && abort_poll(ab, t0)) return;
   }
 }
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
@@ -312,6 +350,13 @@ __device__ __forceinline__ void ldg_stream8(const float* p, float4& a, float4& b
                : "l"(p));
 }
 
+// same load into eight 32-bit registers (f32 bits or packed bf16 pairs)
+__device__ __forceinline__ void ldg_stream8_b32(const void* p, uint32_t* d) {
+  asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]), "=r"(d[4]), "=r"(d[5]), "=r"(d[6]), "=r"(d[7])
+               : "l"(p));
+}
+
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ unsigned ld_relaxed(const unsigned* p) {
   unsigned v;
@@ -319,12 +364,12 @@ __device__ __forceinline__ unsigned ld_relaxed(const unsigned* p) {
   return v;
 }
 // bounded spin with relaxed loads, one acquire fence at the end
-__device__ __forceinline__ void wait_flag_ge_relaxed(const unsigned* p, unsigned target) {
-  if (ld_relaxed(p) < target) {
+__device__ __forceinline__ void wait_flag_ge_relaxed(const unsigned* p, unsigned target, const Abort& ab) {
+  if (ld_relaxed(p) < target && !aborted(ab)) {
     const long long t0 = clock64();
     uint32_t spins = 0;
     while (ld_relaxed(p) < target) {
-      if (((++spins) & 0xFFu) == 0 && (clock64() - t0) > 4000000000ll) __trap();
+      if (((++spins) & 0x3Fu) == 0 && abort_poll(ab, t0)) break;
     }
   }
   __threadfence();

@@ -31,12 +31,15 @@ class IssueEncoder:
     (Embedding(60000,800) -> LSTM 800->2400->2400->2400->800, notebooks/04_Inference.ipynb:157-187)."""
 
     def __init__(self, n_layers: int = 4, emb_sz: int = 800, n_hid: int = 2400, vocab_sz: int = 60000,
-                 pad_idx: int = 1, device: int = 0):
+                 pad_idx: int = 1, device: int = 0, flags: int = 0):
+        """flags: IE_CFG_* bits of include/issue_emb_b200.h (``_lib.IE_CFG_FP32`` = the split-bf16 fp32-accurate mode,
+        ``IE_CFG_ACCURATE_GATES``, ``IE_CFG_F32_GX``); 0 = bf16 operands / f32 accumulate."""
         self._lib = _lib.load()
         self.n_layers, self.emb_sz, self.n_hid, self.vocab_sz, self.pad_idx, self.device = \
             n_layers, emb_sz, n_hid, vocab_sz, pad_idx, device
         self.out_dim = 3 * emb_sz
-        cfg = ie_config(n_layers, emb_sz, n_hid, vocab_sz, pad_idx, device, 0)
+        self.flags = flags
+        cfg = ie_config(n_layers, emb_sz, n_hid, vocab_sz, pad_idx, device, flags)
         h = C.c_void_p()
         check(self._lib.ie_encoder_create(C.byref(cfg), C.byref(h)))
         self._h = h
@@ -117,7 +120,8 @@ class IssueEncoder:
 
     def encode_ids_device(self, ids, lengths, out=None, stream=None):
         """Asynchronous device-resident variant: ids cuda int64 (B,T), lengths cuda int32 (B,), out cuda float32
-        (B, 3*emb_sz); B <= IE_MAX_BATCH.  Runs on `stream` (default: torch's current stream)."""
+        (B, 3*emb_sz); B <= max_batch.  Runs on `stream` (default: torch's current stream).  Data-dependent errors
+        (token id out of range, bad length, device wait timeout) are reported by ``check_errors()``."""
         import torch
         assert ids.is_cuda and lengths.is_cuda and ids.dtype == torch.int64 and lengths.dtype == torch.int32
         ids, lengths = ids.contiguous(), lengths.contiguous()
@@ -128,6 +132,11 @@ class IssueEncoder:
         check(self._lib.ie_encoder_encode(self._h, ids.data_ptr(), lengths.data_ptr(), B, T, out.data_ptr(),
                                           IE_FLAG_DEVICE_PTRS, C.c_void_p(s.cuda_stream)))
         return out
+
+    def check_errors(self) -> None:
+        """Waits for the last call on this handle and raises what its device-side checks found (ValueError for a token
+        id / length out of range, RuntimeError for a device wait timeout).  Host-buffer calls do this themselves."""
+        check(self._lib.ie_encoder_check_errors(self._h))
 
     def raw_features(self, ids) -> np.ndarray:
         """Last layer hidden states (B,T,emb_sz) float32 -- get_raw_features (inference.py:59-68)."""
@@ -143,7 +152,7 @@ class IssueEncoder:
 
     @property
     def max_batch(self) -> int:
-        """Rows one C-ABI encode call takes: IE_MAX_BATCH (768), or 1280 with the experimental IE_ROT=1 kernel."""
+        """Rows one C-ABI encode call takes: 256 x batches per launch (1280 by default, IE_BATCHES=n changes it)."""
         return int(self._lib.ie_encoder_max_batch(self._h))
 
     @property
@@ -161,6 +170,15 @@ class IssueEncoder:
         return dict(gather=v[0], gemm=v[1:1 + 2 * self.n_layers:2], steps=v[2:2 + 2 * self.n_layers:2],
                     finalize=v[1 + 2 * self.n_layers] if n > 1 + 2 * self.n_layers else 0.0)
 
+    def last_phase_mhz(self) -> list:
+        """SM clock (MHz) the recurrent kernel of each layer ran at in the last call (clock64 / globaltimer stamps taken
+        by the kernel itself; nvidia-smi cannot resolve single phases)."""
+        buf = np.zeros(self.n_layers, dtype=np.float32)
+        n = self._lib.ie_encoder_last_phase_mhz(self._h, buf.ctypes.data, buf.size)
+        if n < 0:
+            check(n)
+        return buf[:n].tolist()
+
     # ------------------------------------------------------------------ bulk (df_to_embedding on token ids)
     def encode_id_list(self, docs: List[np.ndarray], bs: int = 100, min_batches_rule: bool = True,
                        coalesce: bool = True) -> np.ndarray:
@@ -168,8 +186,8 @@ class IssueEncoder:
         numericalised docs on: bs = min(bs, N//20+1), argsort by length, right-pad each batch to its own max
         with pad_idx, encode, unsort with argsort(argsort); on RuntimeError (CUDA OOM) halve bs and retry.
         ``coalesce`` (default): consecutive sorted batches are merged into calls of ``max_batch`` rows -- results are
-        independent of batch composition here, so the reference's default ``bs=100`` still reaches the 768-row kernels.
-        Returns (N, 3*emb_sz) float32 in input order."""
-        from .bulk import encode_sorted_batches
-        return encode_sorted_batches(docs, self.encode_ids, self.pad_idx, self.out_dim, bs=bs, max_bs=self.max_batch,
-                                     min_batches_rule=min_batches_rule, coalesce=coalesce)
+        independent of batch composition here, so the reference's default ``bs=100`` still reaches full launches.
+        The loop runs as a device pipeline (pinned double-buffered staging, H2D of batch k+1 under the kernels of batch k,
+        un-sort on the device): ``bulk.encode_sorted_batches_device``.  Returns (N, 3*emb_sz) float32 in input order."""
+        from .bulk import encode_sorted_batches_device
+        return encode_sorted_batches_device(docs, self, bs=bs, min_batches_rule=min_batches_rule, coalesce=coalesce)

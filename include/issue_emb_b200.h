@@ -8,12 +8,18 @@
  *
  * Conventions
  *   - every function returns IE_OK (0) or a negative IE_ERR_* code and never aborts; ie_last_error() returns a
- *     thread-local human-readable message for the last failing call on this thread.
- *   - a handle owns its device weights and workspace; calls on one handle are serialised internally; handles may
- *     be used from any host thread.
+ *     thread-local human-readable message for the last failing call on this thread.  Device-side waits are bounded:
+ *     one that exceeds its limit drains the kernel and surfaces as IE_ERR_CUDA (no trap, the CUDA context and the
+ *     handle stay usable).
+ *   - a handle owns its device weights and workspace; calls on one handle are serialised internally (host mutex; a
+ *     call on another stream first waits for the previous call's completion event); handles may be used from any host
+ *     thread.  The persistent recurrent kernel is launched cooperatively: it runs only when its whole grid can be
+ *     resident, so two handles (or other work) sharing a device serialise instead of deadlocking.
  *   - `flags & IE_FLAG_DEVICE_PTRS`: ids / lengths / out (or X / probs) are device pointers on the handle's
  *     device and the call is asynchronous on `stream`; otherwise they are host pointers (pinned or pageable)
- *     and the call returns after the result has been copied back.
+ *     and the call returns after the result has been copied back.  In device-pointer mode data-dependent errors
+ *     (token id out of range, length outside [1,T] -- clamped --, wait timeout) cannot be returned by the call itself:
+ *     ie_encoder_check_errors() reports them.
  *   - `stream` is a cudaStream_t passed as void*.  With host pointers NULL selects the handle's own stream; with
  *     IE_FLAG_DEVICE_PTRS it is used verbatim (NULL = the legacy default stream, which is torch's default).
  */
@@ -39,10 +45,16 @@ extern "C" {
 /* ie_config.flags */
 #define IE_CFG_ACCURATE_GATES 1 /* ex2+rcp sigmoid/tanh (abs err ~1e-7) instead of the default single-MUFU          */
                                 /* tanh.approx.f32 gates (rel err 2^-11; no measurable effect on the parity metrics) */
+#define IE_CFG_FP32 2           /* "fp32-accurate" mode (BASELINE configs[1] as written; the reference computes in    */
+                                /* fp32, Issue_Embeddings/flask_app/inference.py:57): every product runs as split-bf16  */
+                                /* (x = hi + lo, three tensor-core passes hi*hi + lo*hi + hi*lo, f32 accumulate: ~2^-17 */
+                                /* relative per product), input projections kept in f32, IEEE gates.  ~3x the MMAs.    */
+#define IE_CFG_F32_GX 4         /* keep the hoisted input projections in f32 instead of bf16 (bf16 mode only)         */
 
-#define IE_MAX_BATCH 768 /* rows per ie_encoder_encode call: up to three independent 256-row batches ride one launch of
-                            the persistent recurrent kernel (each a CTA-pair M=256 UMMA tile); they share the kernel,
-                            not their results */
+#define IE_MAX_BATCH 2048 /* upper bound of rows per ie_encoder_encode call; the handle's own limit is
+                             ie_encoder_max_batch() = 256 x (batches per launch, default 5): that many independent
+                             256-row batches ride one launch of the persistent recurrent kernel (each a CTA-pair
+                             M=256 UMMA tile); they share the kernel, not their results */
 
 typedef struct ie_encoder ie_encoder;
 typedef struct ie_mlp ie_mlp;
@@ -85,7 +97,9 @@ int ie_encoder_load_layer(ie_encoder* h, int32_t layer, const float* w_ih, const
  *   lengths [B] int32, 1 <= lengths[b] <= T
  *   out     [B, 3*emb_sz] f32 = [mean | max | last] over the first lengths[b] steps of the last layer's hidden
  *           states, zero initial state (encoder.reset(), inference.py:56)
- * 1 <= B <= IE_MAX_BATCH. */
+ * 1 <= B <= ie_encoder_max_batch(h).  T is bounded only by the workspace cap B_pad*T <= 2^22 tokens (IE_ERR_OOM
+ * beyond; B_pad = B rounded up to 256): the time dimension is processed in chunks, so a single 16k-token issue is
+ * fine. */
 int ie_encoder_encode(ie_encoder* h, const int64_t* ids, const int32_t* lengths, int32_t B, int32_t T, float* out,
                       int32_t flags, void* stream);
 
@@ -96,22 +110,28 @@ int ie_encoder_raw_features(ie_encoder* h, const int64_t* ids, int32_t B, int32_
 /* Number of kernels this handle has launched so far (bench.py reports it as gpu_launches). */
 int64_t ie_encoder_launch_count(const ie_encoder* h);
 
-/* Rows one ie_encoder_encode call accepts on this handle: IE_MAX_BATCH, or 1280 (five 256-row batches per launch;
- * IE_ROT_BATCHES=n, n <= 8, changes that to 256 n) when the experimental rotating-schedule recurrent kernel was enabled
- * with the environment variable IE_ROT=1 at create time (csrc/lstm_rot.cu; off by default). */
+/* Rows one ie_encoder_encode call accepts on this handle: 1280 = five 256-row batches per launch by default
+ * (environment variable IE_BATCHES=n at create time, 1 <= n <= 8, changes that to 256 n). */
 int32_t ie_encoder_max_batch(const ie_encoder* h);
+
+/* Device-side error state of the last call on this handle (waits for it to finish): IE_OK, IE_ERR_TOKEN (a token id
+ * outside [0, vocab_sz) was remapped to 0), IE_ERR_INVALID (a length outside [1,T] was clamped; device-pointer mode
+ * only -- host lengths are validated before anything is launched) or IE_ERR_CUDA (a device-side wait timed out and
+ * the kernel was drained).  Host-pointer calls report these themselves; device-pointer calls are asynchronous, so
+ * their caller asks here.  Clears the state. */
+int ie_encoder_check_errors(ie_encoder* h);
 
 /* Device time of each phase of the last encode call on this handle, from CUDA events recorded on the launching
  * stream: ms[0] = embedding gather, then per layer l: ms[1+2l] = input-projection GEMM, ms[2+2l] = the T recurrent
  * step launches, last = pool finalize.  Waits for the call to finish.  Returns the number of phases (or < 0). */
 int ie_encoder_last_phase_ms(ie_encoder* h, float* ms, int32_t cap);
 
-/* Debug hook: per-step timeline of one layer of the persistent recurrent kernel (tools/trace_seq.py). */
-int64_t ie_debug_seq_trace(ie_encoder* h, int32_t layer, long long* out, int64_t cap);
+/* SM clock (MHz) the recurrent kernel of each layer ran at in the last call, from clock64 / globaltimer stamps taken
+ * by the kernel itself (nvidia-smi cannot resolve single phases).  mhz[l], l < n_layers.  Returns n_layers (or < 0). */
+int ie_encoder_last_phase_mhz(ie_encoder* h, float* mhz, int32_t cap);
 
-/* Debug hook: issue / execution cycles of back-to-back tcgen05.mma (tools/umma_rate.py). */
-int ie_debug_umma_rate(int32_t mode, int32_t n, int32_t iters, int32_t commit_every, int32_t grid, int32_t ntiles,
-                       long long* out2);
+/* Debug hook: per-item timeline of one layer of the persistent recurrent kernel (tools/trace_layer.py). */
+int64_t ie_debug_seq_trace(ie_encoder* h, int32_t layer, long long* out, int64_t cap);
 
 /* MLP head.  Replaces sklearn MLPClassifier.predict_proba as called by MLPWrapper.predict_probabilities
  * (py/label_microservice/mlp.py:56-63): relu hidden layers, logistic output (multilabel).

@@ -227,7 +227,7 @@ def test_bench_clock_sampler_summary():
 
 
 def _rot_schedule_model(T, ng, tiles, P, mma, lat, slots=2):
-    """Event model of csrc/lstm_rot.cu's schedule: item n = t*C + g*tiles + j (C = ng*tiles) runs on CTA pair n % P, pairs
+    """Event model of csrc/lstm_layer.cu's schedule: item n = t*C + g*tiles + j (C = ng*tiles) runs on CTA pair n % P, pairs
     walk their items in increasing n; an item's MMAs start when the pair is free, every item of (t-1, g) has been
     published (its MMA end + lat) and the pair's item `slots` positions back has left its TMEM slot (MMA end + lat).
     Returns (makespan, items seen, True if every dependency had a smaller index)."""
@@ -256,7 +256,7 @@ def _rot_schedule_model(T, ng, tiles, P, mma, lat, slots=2):
 
 
 def test_rotating_schedule_model():
-    """Design claims of DESIGN.md section 4 / csrc/lstm_rot.cu, checked on a timing model: every (t, batch, tile) item is
+    """Design claims of DESIGN.md section 4 / csrc/lstm_layer.cu, checked on a timing model: every (t, batch, tile) item is
     dealt exactly once, an item only waits for smaller indices (=> no wait cycle for ANY pair count), and with five
     batches at H = 2400 (C = 190 >= 2*74 + 38) the pairs issue back to back (within 2 % of 38*mma/74 per batch-step)
     although each item's inputs take `lat` to become visible, while three batches leave that latency exposed."""
@@ -304,7 +304,7 @@ def test_c_abi_from_plain_c(tmp_path):
                     "-l:" + os.path.basename(_lib.LIB_PATH), "-Wl,-rpath," + libdir], check=True)
     r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
-    assert "version=100 symbols=18" in r.stdout, r.stdout
+    assert "version=200 symbols=19" in r.stdout, r.stdout
 
 
 def test_spacy_like_tokenizer_never_loses_characters():

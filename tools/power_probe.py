@@ -2,12 +2,13 @@
 compare energy per FLOP of the encoder paths with cuBLAS (the chip sits at its power cap under all of them,
 profiles/README.md "The kernel runs at the board's power cap").
 
-    python tools/power_probe.py --what cublas,wide,rot --seconds 4 [--T 512]
+    python tools/power_probe.py --what cublas,enc,enc:IE_GX_BF16=0,enc256 --seconds 4 [--T 512]
 
-    cublas : torch.matmul bf16 8192^3 (the driver's MEASURED_PEAKS recipe)
-    wide   : default encoder path, 768 rows x T per call (lstm_wide_kernel + CTA-pair GEMM)
-    rot    : IE_ROT=1 encoder path, 1280 rows x T per call (lstm_rot_kernel)
-    single : default encoder path, 256 rows x T per call (lstm_seq_kernel, one batch)
+    cublas            : torch.matmul bf16 8192^3 (the driver's MEASURED_PEAKS recipe)
+    enc[:K=V[+K=V]]   : encoder path at max_batch rows x T per call, created under the given development knobs
+    enc256[:...]      : same with 256 rows per call (one batch per launch)
+Reports, per workload: median SM clock / board power (nvidia-smi), TFLOP/s, pJ/FLOP, the phase times of the last call
+and the SM clock each layer's recurrent kernel saw (clock64 / globaltimer stamps inside the kernel).
 """
 import argparse
 import json
@@ -76,12 +77,13 @@ def run(what, seconds, T):
         extra = {}
     else:
         from code_intelligence_b200 import IssueEncoder
-        if what == "rot":
-            os.environ["IE_ROT"] = "1"
+        name, _, knobs = what.partition(":")
+        env = dict(kv.split("=") for kv in knobs.split("+")) if knobs else {}
+        os.environ.update(env)
         enc = IssueEncoder().load_weights(*rand_weights())
-        os.environ.pop("IE_ROT", None)
-        B = {"wide": 768, "rot": 1280, "single": 256}[what]
-        assert B <= enc.max_batch, (B, enc.max_batch)
+        for k in env:
+            os.environ.pop(k, None)
+        B = 256 if name == "enc256" else enc.max_batch
         ids = torch.randint(2, 60000, (B, T), dtype=torch.int64, device="cuda")
         lengths = torch.full((B,), T, dtype=torch.int32, device="cuda")
         out = torch.empty((B, enc.out_dim), dtype=torch.float32, device="cuda")
@@ -115,12 +117,13 @@ def run(what, seconds, T):
         rec["issues_per_s"] = round(extra["rows"] * n / (ms * 1e-3), 1)
         rec["phases_last_call"] = {k: ([round(x, 2) for x in v] if isinstance(v, list) else round(v, 2))
                                    for k, v in enc.last_phase_ms().items()}
+        rec["recurrent_kernel_sm_mhz"] = [round(x) for x in enc.last_phase_mhz()]
     return rec
 
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--what", default="cublas,wide,rot")
+    ap.add_argument("--what", default="cublas,enc")
     ap.add_argument("--seconds", type=float, default=4.0)
     ap.add_argument("--T", type=int, default=512)
     a = ap.parse_args()

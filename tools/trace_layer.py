@@ -1,4 +1,4 @@
-"""Development aid: per-item timeline of the rotating-schedule recurrent kernel (IE_ROT, csrc/lstm_rot.cu).
+"""Development aid: per-item timeline of the persistent recurrent kernel (csrc/lstm_layer.cu).
 
 Slots per (cta, item k): 0 step counter seen by the h producer, 1 last h tile issued, 2 first h tile landed (MMA
 thread), 3 MMAs issued + commit, 4 accumulator seen by the epilogue, 5 epilogue stores done, 6 published, 7 c loaded;
@@ -7,7 +7,6 @@ the TMEM slot.  Times are %globaltimer ns.
 """
 import argparse, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-os.environ["IE_ROT"] = os.environ.get("IE_ROT", "2")
 import numpy as np, torch
 from code_intelligence_b200 import IssueEncoder
 
