@@ -413,7 +413,7 @@ def main():
                          "avg_launch_us": avg_launch_ms * 1e3, "flop_per_launch": flop_per_launch,
                          "whole_step_tflops": FLOP_PER_TOKEN * B * T / (ms_max / K * 1e-3) / 1e12,
                          "whole_step_frac": FLOP_PER_TOKEN * B * T / (ms_max / K * 1e-3) / 1e12 / peak,
-                         "phase_ms_last_call": phases, "recurrent_kernel_sm_mhz": [round(x) for x in phase_mhz]},
+                         "phase_ms_last_call": phases, "phase_sm_mhz": {k: [round(x) for x in v] for k, v in phase_mhz.items()}},
             "extra": extra,
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -134,6 +134,7 @@ def encode_sorted_batches_device(docs: List[np.ndarray], enc, bs: int = 100, min
                 if bs == 1:
                     raise Exception(e)
                 bs = max(1, nb // 2)                 # halve what was actually attempted and retry the same position
+                st.h2d_done.synchronize()            # the staging buffer is about to be re-packed
                 continue
             st.compute_done.record(cur)
             st.used = True

@@ -99,7 +99,8 @@ struct ie_encoder {
   std::vector<Layer> layers;
   int segs = 1;            // 1: bf16 operands; 3: split-bf16 ("fp32-accurate", IE_CFG_FP32)
   int gate_mode = 2;       // lstm_common.cuh: 2 tanh.approx, 1 ex2+rcp, 0 IEEE
-  int gx_bf16 = 1;         // input projections (Gx, per-token table) stored as bf16 (f32 in the fp32-accurate mode)
+  int gx_bf16 = 1;         // input projections (Gx, per-token table) stored as 16-bit floats -- IEEE half -- instead of f32
+                           // (f32 in the fp32-accurate mode)
   int use_persistent = 1;  // cooperative persistent kernel; 0 (IE_SEQ=0 or not co-resident): per-timestep fallback
   int persist_checked = 0;
   int cooperative = 1;     // launch attribute (IE_COOP=0: plain launch, co-residency by the occupancy check only)
@@ -235,7 +236,7 @@ int ensure_workspace(ie_encoder* h, int b_pad, int T, int chunk_T, bool want_raw
   CK(h->len_in.reserve(h->max_batch * sizeof(int)));
   CK(h->lengths.reserve(h->max_batch * sizeof(int)));
   CK(h->err.reserve(kErrWords * sizeof(int), true));
-  CK(h->diag.reserve(static_cast<size_t>(c.n_layers) * 4 * sizeof(long long), true));
+  CK(h->diag.reserve(static_cast<size_t>(c.n_layers) * 8 * sizeof(long long), true));
   if (need_x0) CK(h->x0.reserve(static_cast<size_t>(crow) * ring_mul * h->e_pad * sizeof(__nv_bfloat16)));
   // hidden-state rings of one chunk: (chunk_T + 1) slots of b_pad rows; slot 0 = the layer's h before the chunk (carry).
   // Every column a tensor map can reach is written before it is read (padded units produce exact zeros).
@@ -287,7 +288,7 @@ void fill_gemm(const ie_encoder* h, const Layer& L, ie::GemmArgs& g) {
   g.n_store = 4 * L.out_pad;
   g.bn = L.bn;
   g.act = 0;
-  g.out_bf16 = h->gx_bf16;
+  g.out_bf16 = h->gx_bf16 ? 2 : 0;  // fp16 or f32
   g.num_sms = h->num_sms;
   g.segs = h->segs;
   g.abort_flag = h->err.as<unsigned>() + 1;
@@ -358,6 +359,7 @@ int run_encoder(ie_encoder* h, const int64_t* ids, const int32_t* lengths, int B
   if (h->has_done && h->last_stream != s) CK(cudaStreamWaitEvent(s, h->done_ev, 0));
 
   CK(cudaMemsetAsync(h->err.p, 0, kErrWords * sizeof(int), s));
+  CK(cudaMemsetAsync(h->diag.p, 0, static_cast<size_t>(c.n_layers) * 8 * sizeof(long long), s));
   if (pooled) {
     if (lengths == nullptr) return fail(IE_ERR_INVALID, "lengths is null");
     const int* len_src = lengths;
@@ -430,6 +432,7 @@ int run_encoder(ie_encoder* h, const int64_t* ids, const int32_t* lengths, int B
         g.d = h->gx.p;
         g.m_pad = static_cast<int>(crow);
         g.m_store = static_cast<int>(crow);
+        g.diag = h->diag.as<long long>() + 8 * l + 4;
         CK(ie::launch_gemm_bf16(g, s));
         h->launches++;
       }
@@ -453,7 +456,7 @@ int run_encoder(ie_encoder* h, const int64_t* ids, const int32_t* lengths, int B
         q.ldy = h->y_ld; q.raw_ld = L.out_pad;
         q.gate_mode = h->gate_mode; q.gx_bf16 = h->gx_bf16; q.segs = h->segs;
         q.num_sms = h->num_sms; q.check_only = 0; q.cooperative = h->cooperative; q.fault = h->fault;
-        q.diag = h->diag.as<long long>() + 4 * l;
+        q.diag = h->diag.as<long long>() + 8 * l;
         q.trace = nullptr;
         if (l == h->trace_layer && t0 == 0) {
           const int pairs = ie::lstm_layer_pairs(q);
@@ -736,13 +739,16 @@ int ie_encoder_last_phase_mhz(ie_encoder* h, float* mhz, int32_t cap) {
   if (!h->has_done) return fail(IE_ERR_STATE, "no encode call recorded");
   CK(cudaSetDevice(h->cfg.device));
   CK(cudaEventSynchronize(h->done_ev));
-  std::vector<long long> d(static_cast<size_t>(h->cfg.n_layers) * 4);
+  const int L = h->cfg.n_layers;
+  std::vector<long long> d(static_cast<size_t>(L) * 8);
   CK(cudaMemcpy(d.data(), h->diag.p, d.size() * sizeof(long long), cudaMemcpyDeviceToHost));
-  for (int l = 0; l < h->cfg.n_layers && l < cap; ++l) {
-    const long long dc = d[4 * l + 2] - d[4 * l], dn = d[4 * l + 3] - d[4 * l + 1];
-    mhz[l] = dn > 0 ? static_cast<float>(1e3 * static_cast<double>(dc) / static_cast<double>(dn)) : 0.0f;
+  // mhz[l] = recurrent kernel of layer l, mhz[L + l] = its input-projection GEMM (0 when the layer had none)
+  for (int i = 0; i < 2 * L && i < cap; ++i) {
+    const long long* q = d.data() + 8 * (i % L) + 4 * (i / L);
+    const long long dc = q[2] - q[0], dn = q[3] - q[1];
+    mhz[i] = (dn > 0 && dc > 0) ? static_cast<float>(1e3 * static_cast<double>(dc) / static_cast<double>(dn)) : 0.0f;
   }
-  return h->cfg.n_layers;
+  return 2 * h->cfg.n_layers;
 }
 
 // ---------------------------------------------------------------------------------------------

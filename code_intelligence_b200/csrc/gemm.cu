@@ -16,12 +16,20 @@
 //   warps 4..7  epilogue    : tcgen05.ld -> +bias -> activation -> global stores; overlaps the next tile's MMAs
 #include <cstdlib>
 
+#include <cuda_fp16.h>
+#include <type_traits>
+
 #include "kernels.h"
 #include "ptx.cuh"
 
 namespace ie {
 
 namespace {
+
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  const __half2 v = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;  // 64 bf16 = 128 B = one swizzle atom
@@ -32,7 +40,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, OutT* __restrict__ D,
                  const float* __restrict__ bias, int m_store, int n_store, long long ldd, int num_m_blocks,
                  int num_n_blocks, int num_k_blocks, int bn, int stages, int panel, int segs, int k_pad,
-                 unsigned* abort_flag, long long spin_limit) {
+                 unsigned* abort_flag, long long spin_limit, long long* diag) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
@@ -56,6 +64,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (diag != nullptr && blockIdx.x == 0) {  // SM clock of this launch = d(clock64) / d(globaltimer)
+      unsigned long long g;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+      diag[0] = clock64();
+      diag[1] = static_cast<long long>(g);
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < stages; ++s) {
@@ -169,6 +183,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               st_global_v8(drow + n + 8 * j, __float_as_uint(v[8 * j]), __float_as_uint(v[8 * j + 1]),
                            __float_as_uint(v[8 * j + 2]), __float_as_uint(v[8 * j + 3]), __float_as_uint(v[8 * j + 4]),
                            __float_as_uint(v[8 * j + 5]), __float_as_uint(v[8 * j + 6]), __float_as_uint(v[8 * j + 7]));
+          } else if constexpr (std::is_same<OutT, __half>::value) {
+            st_global_v8(drow + n, pack_f16x2(v[0], v[1]), pack_f16x2(v[2], v[3]), pack_f16x2(v[4], v[5]),
+                         pack_f16x2(v[6], v[7]), pack_f16x2(v[8], v[9]), pack_f16x2(v[10], v[11]),
+                         pack_f16x2(v[12], v[13]), pack_f16x2(v[14], v[15]));
           } else {
             st_global_v8(drow + n, pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
                          pack_bf16x2(v[6], v[7]), pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]),
@@ -188,6 +206,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
+  if (diag != nullptr && threadIdx.x == 0 && blockIdx.x == 0) {
+    unsigned long long g;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+    diag[2] = clock64();
+    diag[3] = static_cast<long long>(g);
+  }
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -199,9 +223,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 template <typename OutT, int ACT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                      OutT* __restrict__ D, const float* __restrict__ bias, int m_store, int n_store, long long ldd,
+                      const __grid_constant__ CUtensorMap tmD, OutT* __restrict__ D, const float* __restrict__ bias, int m_store, int n_store, long long ldd,
                       int num_m_blocks /* of 256 rows */, int num_n_blocks, int num_k_blocks, int bn, int stages,
-                      int panel, int segs, int k_pad, unsigned* abort_flag, long long spin_limit) {
+                      int panel, int segs, int k_pad, unsigned* abort_flag, long long spin_limit, long long* diag,
+                      int use_tma_store) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
@@ -209,7 +234,11 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   const uint32_t a_bytes = kBlockM * kBlockK * 2;
   const uint32_t b_bytes = static_cast<uint32_t>(bn / 2) * kBlockK * 2;   // this CTA's half of the B tile
   const uint32_t stage_bytes = a_bytes + b_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(stages) * stage_bytes);
+  // 16-bit outputs leave through shared memory + TMA stores: 2 x (128 rows x 64 columns, 128B swizzle) staging tiles
+  const bool kTmaStore = sizeof(OutT) == 2 && use_tma_store != 0;
+  constexpr uint32_t kOutTileBytes = 128 * 128;
+  uint8_t* out_stage = smem + static_cast<size_t>(stages) * stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(out_stage + (kTmaStore ? 2 * kOutTileBytes : 0));
   uint64_t* full_bar = bars;                   // leader's copy is live: 2 arrivals + both CTAs' bytes
   uint64_t* empty_bar = bars + stages;         // per CTA, arrival = the leader's multicast commit
   uint64_t* tfull_bar = bars + 2 * stages;     // per CTA
@@ -228,6 +257,13 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (kTmaStore) tma_prefetch_desc(&tmD);
+    if (diag != nullptr && blockIdx.x == 0) {  // SM clock of this launch = d(clock64) / d(globaltimer)
+      unsigned long long g;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+      diag[0] = clock64();
+      diag[1] = static_cast<long long>(g);
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < stages; ++s) {
@@ -310,6 +346,7 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     const int q = warp - 4;
     int acc = 0;
     uint32_t acc_phase = 0;
+    [[maybe_unused]] int sub = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
       int m_blk, n_blk;
       decode(tile, m_blk, n_blk);
@@ -317,8 +354,51 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       tc_fence_after();
       const int row = m_blk * 256 + static_cast<int>(crank) * kBlockM + q * 32 + lane;
       const bool row_ok = row < m_store;
-      OutT* drow = D + static_cast<long long>(row) * ldd;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * bn);
+      if (kTmaStore) {
+        // Epilogue through shared memory + cp.async.bulk.tensor stores: whole 128-byte lines leave the SM, so the L2
+        // never holds partially written lines (the direct 32-byte stores of round 1 made it fetch them from DRAM:
+        // dram reads ~ bytes written).  Sub-tiles of 64 columns; two staging buffers; thread 128 owns the bulk group.
+        const int r_in = q * 32 + lane;                       // row inside this CTA's 128-row half
+        const int row0 = m_blk * 256 + static_cast<int>(crank) * kBlockM;
+        for (int c0 = 0; c0 < bn; c0 += 64, ++sub) {
+          uint8_t* buf = out_stage + (sub & 1) * kOutTileBytes;
+          if (threadIdx.x == 128) bulk_wait_group_read<1>();  // the store that last read this buffer has drained it
+          named_bar_sync(2, 128);
+          const int ncols = min(64, bn - c0);
+#pragma unroll
+          for (int cc = 0; cc < 64; cc += 16) {
+            if (cc < ncols) {
+              uint32_t r[16];
+              tmem_ld16(taddr + c0 + cc, r);
+              tmem_ld_wait();
+              const int n = n_blk * bn + c0 + cc;
+              uint32_t w[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                float x0 = __uint_as_float(r[2 * j]), x1 = __uint_as_float(r[2 * j + 1]);
+                if (bias != nullptr) { x0 += __ldg(bias + n + 2 * j); x1 += __ldg(bias + n + 2 * j + 1); }
+                if (ACT == 1) { x0 = fmaxf(x0, 0.0f); x1 = fmaxf(x1, 0.0f); }
+                if (ACT == 2) { x0 = sigmoid_acc(x0); x1 = sigmoid_acc(x1); }
+                if constexpr (std::is_same<OutT, __half>::value) w[j] = pack_f16x2(x0, x1);
+                else w[j] = pack_bf16x2(x0, x1);
+              }
+              // 128B swizzle: 16-byte chunk j of row r sits at position j ^ (r & 7)
+              const int j0 = cc >> 3;
+              const uint32_t base = smem_u32(buf) + static_cast<uint32_t>(r_in) * 128u;
+              sts_v4(base + (static_cast<uint32_t>((j0) ^ (r_in & 7)) << 4), w[0], w[1], w[2], w[3]);
+              sts_v4(base + (static_cast<uint32_t>((j0 + 1) ^ (r_in & 7)) << 4), w[4], w[5], w[6], w[7]);
+            }
+          }
+          fence_proxy_async_smem();                           // generic-proxy writes -> visible to the TMA store
+          named_bar_sync(2, 128);
+          if (threadIdx.x == 128) {
+            tma_store_2d(&tmD, buf, n_blk * bn + c0, row0);   // clipped to [m_store, n_store] by the tensor map
+            bulk_commit_group();
+          }
+        }
+      } else {
+      OutT* drow = D + static_cast<long long>(row) * ldd;
       for (int c = 0; c < bn; c += 16) {
         uint32_t r[16];
         tmem_ld16(taddr + c, r);
@@ -340,12 +420,17 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
               st_global_v8(drow + n + 8 * j, __float_as_uint(v[8 * j]), __float_as_uint(v[8 * j + 1]),
                            __float_as_uint(v[8 * j + 2]), __float_as_uint(v[8 * j + 3]), __float_as_uint(v[8 * j + 4]),
                            __float_as_uint(v[8 * j + 5]), __float_as_uint(v[8 * j + 6]), __float_as_uint(v[8 * j + 7]));
+          } else if constexpr (std::is_same<OutT, __half>::value) {
+            st_global_v8(drow + n, pack_f16x2(v[0], v[1]), pack_f16x2(v[2], v[3]), pack_f16x2(v[4], v[5]),
+                         pack_f16x2(v[6], v[7]), pack_f16x2(v[8], v[9]), pack_f16x2(v[10], v[11]),
+                         pack_f16x2(v[12], v[13]), pack_f16x2(v[14], v[15]));
           } else {
             st_global_v8(drow + n, pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
                          pack_bf16x2(v[6], v[7]), pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]),
                          pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
           }
         }
+      }
       }
       // this CTA's 128 epilogue threads are done with accumulator `acc`: one arrival per CTA at the leader
       tc_fence_before();
@@ -356,6 +441,7 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (kTmaStore && threadIdx.x == 128) bulk_wait_group<0>();  // all stores complete before the CTA may exit
   }
 
   __syncwarp();
@@ -364,6 +450,12 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc_pair(tmem_base, 512);
+  }
+  if (diag != nullptr && threadIdx.x == 0 && blockIdx.x == 0) {
+    unsigned long long g;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+    diag[2] = clock64();
+    diag[3] = static_cast<long long>(g);
   }
 }
 
@@ -400,9 +492,18 @@ cudaError_t launch_gemm_bf16(const GemmArgs& g, cudaStream_t stream) {
     e = make_tmap_bf16_2d(&tmBh, g.b, k_inner, g.n_pad, g.ldb, kBlockK, g.bn / 2);
     if (e != cudaSuccess) return e;
     int stages = 8;
+    const char* tma_env = getenv("IE_GEMM_TMA_STORE");            // IE_GEMM_TMA_STORE=0: direct 256-bit stores (A/B runs)
+    const bool tma_store = g.out_bf16 != 0 && !(tma_env && atoi(tma_env) == 0);  // 16-bit outputs: SMEM + TMA stores
     auto pair_smem = [&](int st) {
-      return 1024 + static_cast<size_t>(st) * (kBlockM * kBlockK * 2 + (g.bn / 2) * kBlockK * 2) + (2 * st + 4) * 8 + 32;
+      return 1024 + static_cast<size_t>(st) * (kBlockM * kBlockK * 2 + (g.bn / 2) * kBlockK * 2) +
+             (tma_store ? 2 * 128 * 128 : 0) + (2 * st + 4) * 8 + 32;
     };
+    CUtensorMap tmD = tmA;                                        // placeholder for the f32-output instantiations
+    if (tma_store) {
+      if (g.ldd % 8 || g.n_store % 8) return cudaErrorInvalidValue;
+      e = make_tmap_bf16_2d(&tmD, g.d, static_cast<uint64_t>(g.n_store), static_cast<uint64_t>(g.m_store), g.ldd, 64, 128);
+      if (e != cudaSuccess) return e;
+    }
     while (stages > 2 && pair_smem(stages) > 227 * 1024) --stages;
     const size_t smem = pair_smem(stages);
     const int num_m_blocks = g.m_pad / 256;
@@ -416,11 +517,15 @@ cudaError_t launch_gemm_bf16(const GemmArgs& g, cudaStream_t stream) {
     auto kfn = gemm_bf16_pair_kernel<OUT, ACT>;                                                                   \
     e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));           \
     if (e != cudaSuccess) return e;                                                                               \
-    kfn<<<grid, kGemmThreads, smem, stream>>>(tmA, tmBh, reinterpret_cast<OUT*>(g.d), g.bias, g.m_store,          \
+    kfn<<<grid, kGemmThreads, smem, stream>>>(tmA, tmBh, tmD, reinterpret_cast<OUT*>(g.d), g.bias, g.m_store,     \
                                               g.n_store, g.ldd, num_m_blocks, num_n_blocks, num_k_blocks, g.bn,   \
-                                              stages, panel, segs, g.k_pad, g.abort_flag, spin_limit);            \
+                                              stages, panel, segs, g.k_pad, g.abort_flag, spin_limit, g.diag,     \
+                                              tma_store ? 1 : 0);                                                 \
   } while (0)
-    if (g.out_bf16) {
+    if (g.out_bf16 == 2) {
+      if (g.act != 0) return cudaErrorInvalidValue;
+      IE_LAUNCH_PAIR(__half, 0);
+    } else if (g.out_bf16) {
       if (g.act == 0) IE_LAUNCH_PAIR(__nv_bfloat16, 0);
       else if (g.act == 1) IE_LAUNCH_PAIR(__nv_bfloat16, 1);
       else IE_LAUNCH_PAIR(__nv_bfloat16, 2);
@@ -452,10 +557,13 @@ cudaError_t launch_gemm_bf16(const GemmArgs& g, cudaStream_t stream) {
     if (e != cudaSuccess) return e;                                                                                \
     kfn<<<grid, kGemmThreads, smem, stream>>>(tmA, tmB, reinterpret_cast<OUT*>(g.d), g.bias, g.m_store, g.n_store, \
                                               g.ldd, num_m_blocks, num_n_blocks, num_k_blocks, g.bn, stages, panel,  \
-                                              segs, g.k_pad, g.abort_flag, spin_limit);                            \
+                                              segs, g.k_pad, g.abort_flag, spin_limit, g.diag);                    \
   } while (0)
 
-  if (g.out_bf16) {
+  if (g.out_bf16 == 2) {
+    if (g.act != 0) return cudaErrorInvalidValue;
+    IE_LAUNCH(__half, 0);
+  } else if (g.out_bf16) {
     if (g.act == 0) IE_LAUNCH(__nv_bfloat16, 0);
     else if (g.act == 1) IE_LAUNCH(__nv_bfloat16, 1);
     else IE_LAUNCH(__nv_bfloat16, 2);

@@ -25,11 +25,12 @@ struct GemmArgs {
   int m_store, n_store;
   int bn;        // N tile (multiple of 16, <= 256, divides n_pad)
   int act;       // 0 none, 1 relu, 2 sigmoid
-  int out_bf16;  // 0 -> f32 output, 1 -> bf16 output
+  int out_bf16;  // output type: 0 f32, 1 bf16, 2 fp16 (act must be 0)
   int num_sms;
   int segs;      // 1: bf16 operands; 3: split-bf16 (K loop over [A_hi|A_lo|A_hi] x [B_hi|B_hi|B_lo], ~fp32 products)
   unsigned* abort_flag;  // optional global word raised when a wait exceeds spin_limit (ptx.cuh abort protocol)
   long long spin_limit;  // SM cycles; 0 = default
+  long long* diag;       // optional [4]: {clock64, globaltimer ns} at the start and end of CTA 0
 };
 cudaError_t launch_gemm_bf16(const GemmArgs& g, cudaStream_t stream);
 

@@ -137,7 +137,7 @@ lstm_step_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant
       uint32_t gxw[kCh][kGW];
       float4 cr[kCh];
       if constexpr (GXBF) {
-        const __nv_bfloat16* gxp = reinterpret_cast<const __nv_bfloat16*>(gx) + grow * (4ll * out_pad) + 4ll * (unit0 + hh * 16);
+        const __half* gxp = reinterpret_cast<const __half*>(gx) + grow * (4ll * out_pad) + 4ll * (unit0 + hh * 16);
 #pragma unroll
         for (int ch = 0; ch < kCh; ++ch) ldg_stream8_b32(gxp + ch * 16, &gxw[ch][0]);
       } else {
@@ -163,7 +163,7 @@ lstm_step_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant
         tmem_ld_wait();
         float4 gx4[4];
         if constexpr (GXBF) {
-          gx_unpack_bf16(gxw[ch], gx4);
+          gx_unpack_f16(gxw[ch], gx4);
         } else {
 #pragma unroll
           for (int u = 0; u < 4; ++u)

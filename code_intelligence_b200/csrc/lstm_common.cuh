@@ -6,6 +6,8 @@
 // Issue_Embeddings/flask_app/inference.py:57,68 (gate rows i|f|g|o, c_t = f*c_{t-1} + i*g, h_t = o*tanh(c_t));
 // pooling: inference.py:239 ([mean | max | last] over the first len_i steps).
 #pragma once
+#include <cuda_fp16.h>
+
 #include "ptx.cuh"
 
 namespace ie {
@@ -52,14 +54,14 @@ __device__ __forceinline__ void lstm_cell4(const uint32_t (&acc)[16], const floa
   }
 }
 
-// bf16 x 16 (one 256-bit load) -> the 4 x float4 Gx operands of a chunk
-__device__ __forceinline__ void gx_unpack_bf16(const uint32_t (&p)[8], float4 (&gx)[4]) {
+// fp16 x 16 (one 256-bit load) -> the 4 x float4 Gx operands of a chunk.  The hoisted input projections are stored as
+// IEEE half (11-bit significand: 8x finer than bf16 at the same bytes; |Gx| is O(1), far inside the half range)
+__device__ __forceinline__ void gx_unpack_f16(const uint32_t* p, float4 (&gx)[4]) {
 #pragma unroll
   for (int u = 0; u < 4; ++u) {
-    gx[u].x = __uint_as_float(p[2 * u] << 16);
-    gx[u].y = __uint_as_float(p[2 * u] & 0xFFFF0000u);
-    gx[u].z = __uint_as_float(p[2 * u + 1] << 16);
-    gx[u].w = __uint_as_float(p[2 * u + 1] & 0xFFFF0000u);
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&p[2 * u]));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&p[2 * u + 1]));
+    gx[u] = make_float4(a.x, a.y, b.x, b.y);
   }
 }
 

@@ -83,7 +83,7 @@ struct KArgs {
   int T, t0, T_total, ng, tiles, out_pad, nkb, segs, kh_pad, gate_mode, trace_items, fault;
 };
 
-// TOK: Gx rows are rows of the per-token input-projection table; GXBF: Gx / table stored as bf16
+// TOK: Gx rows are rows of the per-token input-projection table; GXBF: Gx / table stored as fp16 (f32 otherwise)
 template <bool TOK, bool GXBF>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kLThreads, 1)
 lstm_layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ CUtensorMap tm_w,
@@ -309,7 +309,7 @@ lstm_layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constan
       uint32_t gxw[kCh][kGW];
       float4 cr[kCh];
       if constexpr (GXBF) {
-        const __nv_bfloat16* gxp = reinterpret_cast<const __nv_bfloat16*>(a.gx) + grow * (4ll * a.out_pad) + 4ll * unit0;
+        const __half* gxp = reinterpret_cast<const __half*>(a.gx) + grow * (4ll * a.out_pad) + 4ll * unit0;
 #pragma unroll
         for (int ch = 0; ch < kCh; ++ch) ldg_stream8_b32(gxp + ch * 16, &gxw[ch][0]);
       } else {
@@ -338,7 +338,7 @@ lstm_layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constan
         tmem_ld_wait();
         float4 gx4[4];
         if constexpr (GXBF) {
-          gx_unpack_bf16(gxw[ch], gx4);
+          gx_unpack_f16(gxw[ch], gx4);
         } else {
 #pragma unroll
           for (int u = 0; u < 4; ++u)

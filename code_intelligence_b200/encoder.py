@@ -171,13 +171,13 @@ class IssueEncoder:
                     finalize=v[1 + 2 * self.n_layers] if n > 1 + 2 * self.n_layers else 0.0)
 
     def last_phase_mhz(self) -> list:
-        """SM clock (MHz) the recurrent kernel of each layer ran at in the last call (clock64 / globaltimer stamps taken
-        by the kernel itself; nvidia-smi cannot resolve single phases)."""
-        buf = np.zeros(self.n_layers, dtype=np.float32)
+        """SM clock (MHz) the recurrent kernel ('steps') and the input-projection GEMM ('gemm') of each layer ran at in
+        the last call (clock64 / globaltimer stamps taken by the kernels themselves; nvidia-smi cannot resolve phases)."""
+        buf = np.zeros(2 * self.n_layers, dtype=np.float32)
         n = self._lib.ie_encoder_last_phase_mhz(self._h, buf.ctypes.data, buf.size)
         if n < 0:
             check(n)
-        return buf[:n].tolist()
+        return dict(steps=buf[:self.n_layers].tolist(), gemm=buf[self.n_layers:n].tolist())
 
     # ------------------------------------------------------------------ bulk (df_to_embedding on token ids)
     def encode_id_list(self, docs: List[np.ndarray], bs: int = 100, min_batches_rule: bool = True,

@@ -55,6 +55,20 @@ class MLPHead:
             check(self._lib.ie_mlp_predict_proba(self._h, X.ctypes.data, X.shape[0], probs.ctypes.data, 0, None))
         return probs
 
+    def predict_proba_device(self, X, out=None, stream=None):
+        """Asynchronous device-resident variant: X cuda float32 (n, D_in) -> cuda float32 (n, n_labels) on `stream`
+        (default: torch's current stream)."""
+        import torch
+        assert X.is_cuda and X.dtype == torch.float32 and X.dim() == 2 and X.shape[1] == self.dims[0]
+        X = X.contiguous()
+        if out is None:
+            out = torch.empty((X.shape[0], self.dims[-1]), dtype=torch.float32, device=X.device)
+        s = stream if stream is not None else torch.cuda.current_stream(X.device)
+        if X.shape[0]:
+            check(self._lib.ie_mlp_predict_proba(self._h, X.data_ptr(), X.shape[0], out.data_ptr(),
+                                                 _lib.IE_FLAG_DEVICE_PTRS, C.c_void_p(s.cuda_stream)))
+        return out
+
     def close(self):
         if getattr(self, "_h", None):
             self._lib.ie_mlp_destroy(self._h)

@@ -49,7 +49,7 @@ extern "C" {
                                 /* fp32, Issue_Embeddings/flask_app/inference.py:57): every product runs as split-bf16  */
                                 /* (x = hi + lo, three tensor-core passes hi*hi + lo*hi + hi*lo, f32 accumulate: ~2^-17 */
                                 /* relative per product), input projections kept in f32, IEEE gates.  ~3x the MMAs.    */
-#define IE_CFG_F32_GX 4         /* keep the hoisted input projections in f32 instead of bf16 (bf16 mode only)         */
+#define IE_CFG_F32_GX 4         /* keep the hoisted input projections in f32 instead of fp16 (bf16 mode only)         */
 
 #define IE_MAX_BATCH 2048 /* upper bound of rows per ie_encoder_encode call; the handle's own limit is
                              ie_encoder_max_batch() = 256 x (batches per launch, default 5): that many independent
@@ -127,7 +127,8 @@ int ie_encoder_check_errors(ie_encoder* h);
 int ie_encoder_last_phase_ms(ie_encoder* h, float* ms, int32_t cap);
 
 /* SM clock (MHz) the recurrent kernel of each layer ran at in the last call, from clock64 / globaltimer stamps taken
- * by the kernel itself (nvidia-smi cannot resolve single phases).  mhz[l], l < n_layers.  Returns n_layers (or < 0). */
+ * by the kernel itself (nvidia-smi cannot resolve single phases).  mhz[l] = recurrent kernel of layer l,
+ * mhz[n_layers + l] = its input-projection GEMM (0 when the layer had none).  Returns 2 * n_layers (or < 0). */
 int ie_encoder_last_phase_mhz(ie_encoder* h, float* mhz, int32_t cap);
 
 /* Debug hook: per-item timeline of one layer of the persistent recurrent kernel (tools/trace_layer.py). */

@@ -81,8 +81,6 @@ def run(what, seconds, T):
         env = dict(kv.split("=") for kv in knobs.split("+")) if knobs else {}
         os.environ.update(env)
         enc = IssueEncoder().load_weights(*rand_weights())
-        for k in env:
-            os.environ.pop(k, None)
         B = 256 if name == "enc256" else enc.max_batch
         ids = torch.randint(2, 60000, (B, T), dtype=torch.int64, device="cuda")
         lengths = torch.full((B,), T, dtype=torch.int32, device="cuda")
@@ -117,7 +115,10 @@ def run(what, seconds, T):
         rec["issues_per_s"] = round(extra["rows"] * n / (ms * 1e-3), 1)
         rec["phases_last_call"] = {k: ([round(x, 2) for x in v] if isinstance(v, list) else round(v, 2))
                                    for k, v in enc.last_phase_ms().items()}
-        rec["recurrent_kernel_sm_mhz"] = [round(x) for x in enc.last_phase_mhz()]
+        rec["phase_sm_mhz"] = {k: [round(x) for x in v] for k, v in enc.last_phase_mhz().items()}
+        for k in env:
+            os.environ.pop(k, None)
+        enc.close()
     return rec
 
 

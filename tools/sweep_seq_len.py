@@ -1,6 +1,7 @@
 """BASELINE.json configs[2]: var-len bucketed sweep, seq_len 64..2048, bf16 tensor-core path vs the fp32 CPU oracle.
-Per bucket: 512 issues (two batches of 256 per launch), lengths uniform in (T/2, T], right padded to T.
-Prints one JSON line per bucket (copied to profiles/sweep_r1.jsonl)."""
+Per bucket: 1280 issues (five batches of 256 per launch), lengths uniform in (T/2, T], right padded to T; parity of four
+rows against the live oracle (the full-size goldens of tests/golden cover 32..256 rows per shape in the test-suite).
+Prints one JSON line per bucket (copied to profiles/)."""
 import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -13,7 +14,7 @@ emb, layers = ref.export_weights()
 enc = IssueEncoder().load_weights(emb, layers)
 rng = np.random.default_rng(5)
 for T in (64, 128, 256, 512, 1024, 2048):
-    B = 512
+    B = enc.max_batch
     lengths = rng.integers(T // 2 + 1, T + 1, size=B).astype(np.int32)
     ids = np.full((B, T), 1, dtype=np.int64)
     for b in range(B):
@@ -32,10 +33,11 @@ for T in (64, 128, 256, 512, 1024, 2048):
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / n
     got = out.cpu().numpy()
-    sub = [0, 1, 300, 511]
+    sub = [0, 1, 300, B - 1]
     want = R.encode_padded(ref, ids[sub], lengths[sub])
     m = R.parity_metrics(got[sub], want)
     valid_tokens = int(lengths.sum())
     print(json.dumps(dict(seq_len=T, issues=B, ms=ms, issues_per_s=B / ms * 1e3, valid_tokens_per_s=valid_tokens / ms * 1e3,
                           tflops_valid=266.24e6 * valid_tokens / ms / 1e9, tflops_padded=266.24e6 * B * T / ms / 1e9,
-                          min_cosine=m["min_cosine"], max_abs=m["max_abs"], rel_l2=m["rel_l2"])), flush=True)
+                          min_cosine=m["min_cosine"], max_abs=m["max_abs"], rel_l2=m["rel_l2"],
+                          phase_ms=enc.last_phase_ms(), phase_sm_mhz=enc.last_phase_mhz())), flush=True)
