@@ -879,6 +879,45 @@ int ie_mlp_predict_proba(ie_mlp* m, const float* X, int32_t n, float* probs, int
   return IE_OK;
 }
 
+int ie_pr_thresholds(const float* scores, const uint8_t* truth, int32_t n, int32_t n_labels, double precision_threshold,
+                     double recall_threshold, float* thresholds, double* precisions, double* recalls, int32_t device,
+                     int32_t flags, void* stream) {
+  if (scores == nullptr || truth == nullptr || thresholds == nullptr || precisions == nullptr || recalls == nullptr)
+    return fail(IE_ERR_INVALID, "null argument");
+  if (n < 1 || n_labels < 1) return fail(IE_ERR_INVALID, "n=%d n_labels=%d", n, n_labels);
+  if (n > ie::kPrMaxSamples)
+    return fail(IE_ERR_INVALID, "n=%d exceeds the %d samples one CTA sorts in shared memory", n, ie::kPrMaxSamples);
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(IE_ERR_CUDA, "no CUDA device available (%s): this library has no CPU fallback", cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return fail(IE_ERR_INVALID, "device %d not in [0,%d)", device, ndev);
+  CK(cudaSetDevice(device));
+  const bool dev = (flags & IE_FLAG_DEVICE_PTRS) != 0;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (dev) {
+    CK(ie::launch_pr_thresholds(scores, truth, n, n_labels, precision_threshold, recall_threshold, thresholds, precisions,
+                                recalls, s));
+    return IE_OK;
+  }
+  DevBuf ds, dt, dth, dp, dr;
+  const size_t cells = static_cast<size_t>(n) * n_labels;
+  CK(ds.reserve(cells * sizeof(float)));
+  CK(dt.reserve(cells));
+  CK(dth.reserve(n_labels * sizeof(float)));
+  CK(dp.reserve(n_labels * sizeof(double)));
+  CK(dr.reserve(n_labels * sizeof(double)));
+  CK(cudaMemcpyAsync(ds.p, scores, cells * sizeof(float), cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(dt.p, truth, cells, cudaMemcpyHostToDevice, s));
+  CK(ie::launch_pr_thresholds(ds.as<float>(), dt.as<uint8_t>(), n, n_labels, precision_threshold, recall_threshold,
+                              dth.as<float>(), dp.as<double>(), dr.as<double>(), s));
+  CK(cudaMemcpyAsync(thresholds, dth.p, n_labels * sizeof(float), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(precisions, dp.p, n_labels * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(recalls, dr.p, n_labels * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return IE_OK;
+}
+
 void ie_mlp_destroy(ie_mlp* m) {
   if (m == nullptr) return;
   cudaSetDevice(m->device);

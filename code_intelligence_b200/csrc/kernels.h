@@ -111,4 +111,9 @@ cudaError_t launch_convert_rows(const float* src, long long ld_src, int cols, co
                                 __nv_bfloat16* dst, long long ld_dst, int lo_off, cudaStream_t stream);
 cudaError_t launch_fill_f32(float* p, size_t n, float v, cudaStream_t stream);
 
+// ---- precision-recall threshold search (pr_curve.cu): scores [n, n_labels] f32, truth [n, n_labels] u8 (device) ----------
+constexpr int kPrMaxSamples = 16384;
+cudaError_t launch_pr_thresholds(const float* scores, const uint8_t* truth, int n, int n_labels, double p_thr,
+                                 double r_thr, float* out_thr, double* out_prec, double* out_rec, cudaStream_t stream);
+
 }  // namespace ie

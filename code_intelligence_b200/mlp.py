@@ -18,6 +18,43 @@ from . import _lib
 from ._lib import check
 
 
+PR_MAX_SAMPLES = 16384   # ie::kPrMaxSamples
+
+
+def pr_thresholds_host(scores, truth, precision_threshold, recall_threshold):
+    """The reference's per-label loop (mlp.py:81-98) on sklearn's precision_recall_curve -> (thr, prec, rec) lists."""
+    from sklearn.metrics import precision_recall_curve
+    import warnings
+    thr_o, prec_o, rec_o = [], [], []
+    for label in range(truth.shape[1]):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")              # "No positive class found": recall is set to one, as on the GPU
+            prec, rec, thr = precision_recall_curve(truth[:, label], scores[:, label])
+        prec, rec = prec[:-1], rec[:-1]                  # the curve's last point has no threshold
+        ok = (prec >= precision_threshold) & (rec >= recall_threshold) & (prec > 0.0)
+        if ok.any():
+            k = int(np.argmax(np.where(ok, prec, -1.0)))  # first index of the best qualifying precision
+            thr_o.append(float(thr[k])); prec_o.append(float(prec[k])); rec_o.append(float(rec[k]))
+        else:
+            thr_o.append(None); prec_o.append(0.0); rec_o.append(0.0)
+    return thr_o, prec_o, rec_o
+
+
+def pr_thresholds(scores, truth, precision_threshold, recall_threshold, device: int = 0):
+    """Same on the GPU (``ie_pr_thresholds``, csrc/pr_curve.cu): scores (n, L) float32, truth (n, L) 0/1, n <= 16384."""
+    lib = _lib.load()
+    scores = np.ascontiguousarray(scores, dtype=np.float32)
+    truth = np.ascontiguousarray(np.asarray(truth) != 0, dtype=np.uint8)
+    n, L = scores.shape
+    assert truth.shape == (n, L)
+    thr = np.empty(L, dtype=np.float32)
+    prec = np.empty(L, dtype=np.float64)
+    rec = np.empty(L, dtype=np.float64)
+    check(lib.ie_pr_thresholds(scores.ctypes.data, truth.ctypes.data, n, L, float(precision_threshold),
+                               float(recall_threshold), thr.ctypes.data, prec.ctypes.data, rec.ctypes.data, device, 0, None))
+    return [None if np.isnan(t) else float(t) for t in thr], [float(p) for p in prec], [float(r) for r in rec]
+
+
 class MLPHead:
     """Owner of an ``ie_mlp`` handle: weights in sklearn layout (coefs_[l] is [fan_in, fan_out])."""
 
@@ -117,25 +154,22 @@ class MLPWrapper:
         """mlp.py:65-98: hold out ``test_size`` of the data (random_state 1234), fit on the rest, and for every label keep
         the probability threshold with the highest precision among the points of its precision-recall curve that meet
         both ``precision_threshold`` and ``recall_threshold`` (first such point on ties; ``None`` when no point
-        qualifies, which makes the label unpredictable, repo_specific_model.py:138-141)."""
-        from sklearn.metrics import precision_recall_curve
+        qualifies, which makes the label unpredictable, repo_specific_model.py:138-141).  ``fit`` stays on sklearn; the
+        hold-out ``predict_proba`` and the per-label curve search run on the GPU (``ie_pr_thresholds``: sort + prefix sum +
+        argmax per label in one kernel); hold-out sets above 16384 rows use sklearn's curve on the host."""
         from sklearn.model_selection import train_test_split
         X_train, X_test, y_train, y_test = train_test_split(X, y, test_size=test_size, random_state=1234)
         self.fit(X_train, y_train)
         scores = self.predict_probabilities(X_test)
         truth = np.asarray(y_test)
         self.total_labels_count = truth.shape[1]
-        self.probability_thresholds, self.precisions, self.recalls = {}, {}, {}
-        for label in range(self.total_labels_count):
-            prec, rec, thr = precision_recall_curve(truth[:, label], scores[:, label])
-            prec, rec = prec[:-1], rec[:-1]                      # the curve's last point has no threshold
-            ok = (prec >= self.precision_threshold) & (rec >= self.recall_threshold) & (prec > 0.0)
-            if ok.any():
-                k = int(np.argmax(np.where(ok, prec, -1.0)))     # first index of the best qualifying precision
-                chosen = (thr[k], prec[k], rec[k])
-            else:
-                chosen = (None, 0.0, 0.0)
-            self.probability_thresholds[label], self.precisions[label], self.recalls[label] = chosen
+        if truth.shape[0] <= PR_MAX_SAMPLES:
+            thr, prec, rec = pr_thresholds(scores, truth, self.precision_threshold, self.recall_threshold, self._device)
+        else:
+            thr, prec, rec = pr_thresholds_host(scores, truth, self.precision_threshold, self.recall_threshold)
+        self.probability_thresholds = {l: thr[l] for l in range(self.total_labels_count)}
+        self.precisions = {l: prec[l] for l in range(self.total_labels_count)}
+        self.recalls = {l: rec[l] for l in range(self.total_labels_count)}
 
     def grid_search(self, params=None, cv=5, n_jobs=-1):
         from sklearn.model_selection import GridSearchCV

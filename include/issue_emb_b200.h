@@ -143,6 +143,17 @@ int ie_mlp_load_layer(ie_mlp* m, int32_t layer, const float* coef, const float* 
 int ie_mlp_predict_proba(ie_mlp* m, const float* X, int32_t n, float* probs, int32_t flags, void* stream);
 void ie_mlp_destroy(ie_mlp* m);
 
+/* Threshold search.  Replaces the per-label loop of MLPWrapper.find_probability_thresholds
+ * (py/label_microservice/mlp.py:81-98: sklearn precision_recall_curve + "highest precision among the points with
+ * precision >= precision_threshold and recall >= recall_threshold; first such point in increasing-threshold order").
+ *   scores [n, n_labels] f32 (predict_proba of the hold-out set), truth [n, n_labels] uint8 (0/1), n <= 16384
+ *   thresholds [n_labels] f32 (NaN: no qualifying point, the label is excluded -- None in the reference),
+ *   precisions / recalls [n_labels] f64 at the chosen point (0 when excluded).
+ * Host pointers (synchronous) or, with IE_FLAG_DEVICE_PTRS, device pointers on `device` (asynchronous on `stream`). */
+int ie_pr_thresholds(const float* scores, const uint8_t* truth, int32_t n, int32_t n_labels, double precision_threshold,
+                     double recall_threshold, float* thresholds, double* precisions, double* recalls, int32_t device,
+                     int32_t flags, void* stream);
+
 /* Debug / test hook: D[M,N] = A[M,K] * B[N,K]^T (+bias) through the same tcgen05 GEMM the encoder uses.
  * a [M,K], b [N,K], bias [N] or NULL: host f32 (rounded to bf16 on the device); d [M,N] host f32. */
 int ie_debug_gemm(const float* a, const float* b, const float* bias, int32_t M, int32_t N, int32_t K, int32_t act,

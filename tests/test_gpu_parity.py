@@ -547,3 +547,26 @@ def test_mlp_wrapper_matches_sklearn():
         w.fit(X, y)
     Xt = rng.random((300, 12)).astype(np.float32)
     np.testing.assert_allclose(w.predict_probabilities(Xt), clf.predict_proba(Xt), atol=5e-3)
+
+
+def test_threshold_search_on_device_matches_sklearn_loop():
+    """ie_pr_thresholds (csrc/pr_curve.cu) against the reference's per-label loop on sklearn's precision_recall_curve
+    (py/label_microservice/mlp.py:81-98): identical thresholds, precisions, recalls -- with ties in the scores, labels
+    without positives, labels that never qualify, and n that is not a power of two."""
+    from code_intelligence_b200.mlp import pr_thresholds, pr_thresholds_host
+    rng = np.random.default_rng(3)
+    for n, L, quant in ((37, 5, 10), (1000, 40, 50), (5000, 17, 0), (16384, 3, 1000)):
+        truth = (rng.random((n, L)) < rng.uniform(0.02, 0.6, size=L)).astype(np.uint8)
+        signal = rng.uniform(0.0, 3.0, size=L)                         # some labels learnable, some not
+        logits = rng.standard_normal((n, L)) + signal * (truth * 2.0 - 1.0)
+        scores = (1.0 / (1.0 + np.exp(-logits))).astype(np.float32)
+        if quant:
+            scores = (np.round(scores * quant) / quant).astype(np.float32)   # many ties
+        truth[:, 0] = 0                                                 # a label without positives
+        for p_thr, r_thr in ((0.7, 0.5), (0.0, 0.0), (0.99, 0.99)):
+            got = pr_thresholds(scores, truth, p_thr, r_thr)
+            want = pr_thresholds_host(scores, truth, p_thr, r_thr)
+            assert got[0] == want[0], (n, L, quant, p_thr)
+            np.testing.assert_array_equal(np.array(got[1]), np.array(want[1]))
+            np.testing.assert_array_equal(np.array(got[2]), np.array(want[2]))
+        assert want[0][0] is None

@@ -112,6 +112,9 @@ assert np.allclose(out, want, atol=1e-6), np.abs(out - want).max()
 # an empty shard on one rank must still work
 one = bulk.encode_bulk_distributed(docs[:1], local)
 assert np.allclose(one, want[:1], atol=1e-6)
+# the per-rank encoder may hand back a tensor (on the GPU: device resident); to_host=False keeps the result a tensor
+as_t = bulk.encode_bulk_distributed(docs, lambda d: torch.from_numpy(local(d)), to_host=False)
+assert isinstance(as_t, torch.Tensor) and np.array_equal(as_t.numpy(), out)
 dist.destroy_process_group()
 print("rank", sys.argv[1], "ok")
 '''
@@ -304,7 +307,7 @@ def test_c_abi_from_plain_c(tmp_path):
                     "-l:" + os.path.basename(_lib.LIB_PATH), "-Wl,-rpath," + libdir], check=True)
     r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
-    assert "version=200 symbols=19" in r.stdout, r.stdout
+    assert "version=200 symbols=20" in r.stdout, r.stdout
 
 
 def test_spacy_like_tokenizer_never_loses_characters():
