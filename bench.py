@@ -337,6 +337,19 @@ def main():
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     e2e_value = n_total / float(t_e2e.item())
     clocks = sampler.stop() if rank == 0 else None
+    # where the end-to-end time goes (a second, diagnostic repetition on this rank's shard; not part of `e2e.value`)
+    e2e_breakdown = None
+    if world == 1:
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        loc = local_fn(docs)
+        torch.cuda.synchronize(dev)
+        t1 = time.perf_counter()
+        host = loc.cpu().numpy()
+        t2 = time.perf_counter()
+        e2e_breakdown = {"pack_h2d_encode_unsort_ms": (t1 - t0) * 1e3, "d2h_result_ms": (t2 - t1) * 1e3,
+                         "device_only_ms_for_same_steps": ms_max}
+        del loc, host
 
     # ---- extras (rank 0 reports; all ranks take part where a collective is involved) ---------------------------
     extra = {}
@@ -402,7 +415,8 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "issues/s", "h2d_bytes_per_step": B * T * 8 + B * 4,
                     "d2h_bytes_per_step": world * B * 3 * EMB * 4,
-                    "api": "bulk.encode_bulk_distributed(host id lists) -> np.ndarray (N, 2400)"},
+                    "api": "bulk.encode_bulk_distributed(host id lists) -> np.ndarray (N, 2400)",
+                    "breakdown_ms": e2e_breakdown},
             "single_batch": {"value": single_value, "unit": "issues/s", "ms_per_step": ms_single / K,
                              "note": "same measurement with one batch of 256 per launch"},
             "gpu_launches": int(launches),

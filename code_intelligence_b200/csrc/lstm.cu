@@ -180,8 +180,12 @@ lstm_step_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant
           float4* rp = reinterpret_cast<float4*>(raw + (static_cast<long long>(brow) * T_total + tg) * raw_ld + unit0 + uo);
           *rp = make_float4(hn[0], hn[1], hn[2], hn[3]);
         }
-        if (pooled)
-          pool_accumulate4(pool_sum, pool_max, pool_last, static_cast<long long>(brow) * out_pad + unit0 + uo, hn, tg, len);
+        if (pooled) {
+          const long long po = static_cast<long long>(brow) * out_pad + unit0 + uo;
+          const float4 mprev = (tg > 0 && tg < len) ? __ldcg(reinterpret_cast<const float4*>(pool_max + po))
+                                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+          pool_accumulate4(pool_sum, pool_max, pool_last, po, hn, mprev, tg, len);
+        }
       }
     }
   }

@@ -66,14 +66,35 @@ __device__ __forceinline__ void gx_unpack_f16(const uint32_t* p, float4 (&gx)[4]
 }
 
 // ---- masked concat-pool accumulators in global memory ------------------------------------------------------------
-// pool_sum : f32, sequential sum over t (one add per timestep, in timestep order)
-// pool_max : f32 encoded as an order-preserving u32 (enc_max / dec_max) so that the running max is a fire-and-forget
-//            red.max.u32
+// pool_sum : f32, sequential sum over t (one add per timestep, in timestep order): an L2 reduction (red.add.v4.f32) --
+//            no load, no latency, no accumulator registers.  The (step, batch) counter protocol of the persistent kernel
+//            orders step t's reduction after step t-1's (gpu-scope fence before the counter increment), so it is the same
+//            sequential f32 sum a register accumulator would give: identical bits on every path.
+// pool_max : f32 running max; it travels like the cell state (the caller loads the previous value from L2 before the
+//            accumulator is ready and this function stores the new one) -- 16 scalar red.max per thread and item put
+//            ~6 us of L2 atomic traffic on the last layer's step chain.
 // pool_last: f32, h at t == len-1
-// At t == 0 the accumulators are initialised with plain stores; for t > 0 the updates are reductions performed by the
-// L2 (no load, no latency on the step's critical path, no accumulator registers).  The (step, batch) counter
-// protocol of the persistent kernel orders step t's reductions after step t-1's (gpu-scope fence before the counter
-// increment), so the f32 sum is the same sequential sum a register accumulator would give: identical bits on every path.
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+// po: offset of the 4 units in the [row, out_pad] accumulator arrays; mprev: pool_max[po..po+3] (read when 0 < tg < len);
+// tg: global timestep; len: valid length of the row
+__device__ __forceinline__ void pool_accumulate4(float* pool_sum, float* pool_max, float* pool_last, long long po,
+                                                 const float (&hn)[4], const float4& mprev, int tg, int len) {
+  if (tg >= len) return;
+  const float4 h4 = make_float4(hn[0], hn[1], hn[2], hn[3]);
+  if (tg == 0) {
+    __stcg(reinterpret_cast<float4*>(pool_sum + po), h4);
+    __stcg(reinterpret_cast<float4*>(pool_max + po), h4);
+  } else {
+    red_add_v4(pool_sum + po, hn[0], hn[1], hn[2], hn[3]);
+    __stcg(reinterpret_cast<float4*>(pool_max + po),
+           make_float4(fmaxf(mprev.x, hn[0]), fmaxf(mprev.y, hn[1]), fmaxf(mprev.z, hn[2]), fmaxf(mprev.w, hn[3])));
+  }
+  if (tg == len - 1) __stcg(reinterpret_cast<float4*>(pool_last + po), h4);
+}
+
+// order-preserving u32 encoding of f32 (used by pr_curve.cu to sort scores as integers)
 __device__ __forceinline__ uint32_t enc_max(float x) {
   const uint32_t b = __float_as_uint(x);
   return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
@@ -87,27 +108,6 @@ __host__ __device__ __forceinline__ float dec_max(uint32_t e) {
   memcpy(&f, &b, 4);
   return f;
 #endif
-}
-__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
-  asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
-__device__ __forceinline__ void red_max_u32(uint32_t* p, uint32_t v) {
-  asm volatile("red.relaxed.gpu.global.max.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-// po: offset of the 4 units in the [row, out_pad] accumulator arrays; tg: global timestep; len: valid length of the row
-__device__ __forceinline__ void pool_accumulate4(float* pool_sum, float* pool_max, float* pool_last, long long po,
-                                                 const float (&hn)[4], int tg, int len) {
-  if (tg >= len) return;
-  uint32_t* pm = reinterpret_cast<uint32_t*>(pool_max) + po;
-  if (tg == 0) {
-    __stcg(reinterpret_cast<float4*>(pool_sum + po), make_float4(hn[0], hn[1], hn[2], hn[3]));
-    __stcg(reinterpret_cast<uint4*>(pm), make_uint4(enc_max(hn[0]), enc_max(hn[1]), enc_max(hn[2]), enc_max(hn[3])));
-  } else {
-    red_add_v4(pool_sum + po, hn[0], hn[1], hn[2], hn[3]);
-#pragma unroll
-    for (int u = 0; u < 4; ++u) red_max_u32(pm + u, enc_max(hn[u]));
-  }
-  if (tg == len - 1) __stcg(reinterpret_cast<float4*>(pool_last + po), make_float4(hn[0], hn[1], hn[2], hn[3]));
 }
 
 // h_t in the ring: bf16 (hi); with `lo_off` > 0 also the bf16 residual h - hi at column offset lo_off (the split-bf16

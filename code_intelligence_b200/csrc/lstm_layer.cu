@@ -39,8 +39,7 @@ namespace ie {
 namespace {
 
 constexpr int kLThreads = 640;          // 4 role warps + 16 epilogue warps (4 per TMEM lane quarter, 64 columns each)
-constexpr int kLGA = 2, kLAStages = 3;  // h ring: 3 stages x 2 k-blocks x 16 KB
-constexpr int kLGW = 2, kLWStages = 3;  // W ring: 3 stages x 2 k-blocks x 16 KB
+constexpr int kLStages = 7;             // operand ring: 7 stages x (h k-block 16 KB + W_hh k-block 16 KB) per CTA
 constexpr int kLTileN = 256;            // accumulator columns per tile = 64 hidden units
 constexpr int kLHalfRows = 128;         // W rows each CTA of the pair contributes
 
@@ -83,8 +82,9 @@ struct KArgs {
   int T, t0, T_total, ng, tiles, out_pad, nkb, segs, kh_pad, gate_mode, trace_items, fault;
 };
 
-// TOK: Gx rows are rows of the per-token input-projection table; GXBF: Gx / table stored as fp16 (f32 otherwise)
-template <bool TOK, bool GXBF>
+// TOK: Gx rows are rows of the per-token input-projection table; GXBF: Gx / table stored as fp16 (f32 otherwise);
+// POOL: last layer -- the masked concat-pool accumulators ride the epilogue
+template <bool TOK, bool GXBF, bool POOL>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kLThreads, 1)
 lstm_layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ CUtensorMap tm_w,
                   const __grid_constant__ KArgs a) {
@@ -94,14 +94,16 @@ lstm_layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constan
 
   constexpr uint32_t a_bytes = 128 * 64 * 2;
   constexpr uint32_t w_bytes = kLHalfRows * 64 * 2;
-  uint8_t* a_ring = smem;
-  uint8_t* w_ring = smem + kLAStages * kLGA * a_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(w_ring + kLWStages * kLGW * w_bytes);
-  uint64_t* afull = bars;                   // [kLAStages] leader's copy is live
-  uint64_t* aempty = afull + kLAStages;
-  uint64_t* wfull = aempty + kLAStages;     // [kLWStages]
-  uint64_t* wempty = wfull + kLWStages;
-  uint64_t* tfull = wempty + kLWStages;     // [2] accumulator slot holds a finished item (both CTAs' copies live)
+  constexpr uint32_t stage_bytes = a_bytes + w_bytes;
+  // ONE ring for both operands (like the GEMM main loop): stage s holds the k-block's h tile and W_hh tile.  The two
+  // producers fill their halves independently -- W_hh does not depend on the step, so its producer runs ahead of the h
+  // dependency -- and the MMA thread waits on one barrier and commits once per k-block.  (Round 1's two 3 x 2-k-block
+  // rings left ~18 % of the MMA thread's time in stage waits: a stage was only refilled after both of its k-blocks.)
+  uint8_t* ring = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + kLStages * stage_bytes);
+  uint64_t* full = bars;                    // [kLStages] leader's copy is live: 4 arrivals (h / W producer of each CTA)
+  uint64_t* empty = full + kLStages;        // [kLStages] per CTA: the leader's multicast commit
+  uint64_t* tfull = empty + kLStages;       // [2] accumulator slot holds a finished item (both CTAs' copies live)
   uint64_t* tempty = tfull + 2;             // [2] accumulator slot drained by both CTAs (leader's copy is live)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
   uint32_t* cready = tmem_slot + 1;         // number of this CTA's items whose (t-1, g) counter the watcher has seen
@@ -138,13 +140,9 @@ lstm_layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constan
     }
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < kLAStages; ++s) {
-      mbar_init(&afull[s], 2);
-      mbar_init(&aempty[s], 1);
-    }
-    for (int s = 0; s < kLWStages; ++s) {
-      mbar_init(&wfull[s], 2);
-      mbar_init(&wempty[s], 1);
+    for (int s = 0; s < kLStages; ++s) {
+      mbar_init(&full[s], 4);
+      mbar_init(&empty[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull[s], 1);
@@ -174,18 +172,14 @@ lstm_layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constan
         if (t > 0) fence_proxy_async();  // h_{t-1} was written through the generic proxy, TMA reads it
         IE_TRACE(0, k);
         const int row0 = t * b_pad + g * 256 + static_cast<int>(crank) * 128;  // ring slot t = h_{t-1} (chunk-local)
-        for (int kb0 = 0; kb0 < nkt; kb0 += kLGA) {
-          const int nb = min(kLGA, nkt - kb0);
-          mbar_wait(&aempty[stage], phase ^ 1, ab);
-          if (crank == 0) mbar_arrive_expect_tx(&afull[stage], 2 * nb * a_bytes);
-          else mbar_arrive_remote(&afull[stage], 0);
-          for (int q = 0; q < nb; ++q) {
-            const int kb = kb0 + q;
-            const int seg = kb / a.nkb, r = kb - seg * a.nkb;          // split-bf16: [h_hi | h_lo | h_hi]
-            tma_load_2d_pair(a_ring + (stage * kLGA + q) * a_bytes, &tm_h, &afull[stage],
-                             (seg == 1 ? a.kh_pad : 0) + r * 64, row0, kEvictNormal);
-          }
-          if (++stage == kLAStages) { stage = 0; phase ^= 1; }
+        for (int kb = 0; kb < nkt; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1, ab);
+          if (crank == 0) mbar_arrive_expect_tx(&full[stage], 2 * a_bytes);
+          else mbar_arrive_remote(&full[stage], 0);
+          const int seg = kb / a.nkb, r = kb - seg * a.nkb;            // split-bf16: [h_hi | h_lo | h_hi]
+          tma_load_2d_pair(ring + stage * stage_bytes, &tm_h, &full[stage], (seg == 1 ? a.kh_pad : 0) + r * 64, row0,
+                           kEvictNormal);
+          if (++stage == kLStages) { stage = 0; phase ^= 1; }
         }
         IE_TRACE(1, k);
       }
@@ -211,18 +205,14 @@ lstm_layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constan
       for (long long n = pair; n < total && !aborted(ab); n += P) {
         const int j = static_cast<int>(n % C) % tiles;
         const int wrow0 = (2 * j + static_cast<int>(crank)) * kLHalfRows;  // slices are [cta][unit][gate], 128 rows each
-        for (int kb0 = 0; kb0 < nkt; kb0 += kLGW) {
-          const int nb = min(kLGW, nkt - kb0);
-          mbar_wait(&wempty[stage], phase ^ 1, ab);
-          if (crank == 0) mbar_arrive_expect_tx(&wfull[stage], 2 * nb * w_bytes);
-          else mbar_arrive_remote(&wfull[stage], 0);
-          for (int q = 0; q < nb; ++q) {
-            const int kb = kb0 + q;
-            const int seg = kb / a.nkb, r = kb - seg * a.nkb;          // split-bf16: [W_hi | W_hi | W_lo]
-            tma_load_2d_pair(w_ring + (stage * kLGW + q) * w_bytes, &tm_w, &wfull[stage],
-                             (seg == 2 ? a.kh_pad : 0) + r * 64, wrow0, kEvictLast);
-          }
-          if (++stage == kLWStages) { stage = 0; phase ^= 1; }
+        for (int kb = 0; kb < nkt; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1, ab);
+          if (crank == 0) mbar_arrive_expect_tx(&full[stage], 2 * w_bytes);
+          else mbar_arrive_remote(&full[stage], 0);
+          const int seg = kb / a.nkb, r = kb - seg * a.nkb;            // split-bf16: [W_hi | W_hi | W_lo]
+          tma_load_2d_pair(ring + stage * stage_bytes + a_bytes, &tm_w, &full[stage], (seg == 2 ? a.kh_pad : 0) + r * 64,
+                           wrow0, kEvictLast);
+          if (++stage == kLStages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -230,52 +220,36 @@ lstm_layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constan
     // ---------------- UMMA issuer (leader CTA) --------------------------------------------------------------
     if (crank == 0 && lane == 0) {
       const uint32_t idesc = umma_idesc_bf16(256, kLTileN);
-      const uint32_t a_base = smem_u32(a_ring);
-      const uint32_t w_base = smem_u32(w_ring);
-      int as = 0, ws = 0;
-      uint32_t aph = 0, wph = 0;
+      const uint32_t ring_base = smem_u32(ring);
+      int st = 0;
+      uint32_t ph = 0;
       int k = 0;
       for (long long n = pair; n < total && !aborted(ab); n += P, ++k) {
         const int slot = k & 1;
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(slot * kLTileN);
-        long long wa = 0, ww = 0, t_first = 0;
+        long long wa = 0, t_first = 0;
         if (k >= 2) {  // the slot's previous item (k - 2) must have been read out of TMEM by both CTAs
           const long long c0 = trace ? clock64() : 0;
           mbar_wait(&tempty[slot], static_cast<uint32_t>(((k >> 1) - 1) & 1), ab);
           IE_TRACE_VAL(11, k, trace ? clock64() - c0 : 0);
         }
         for (int kb = 0; kb < nkt; ++kb) {
-          const int ja = kb % kLGA, jw = kb % kLGW;
-          if (ja == 0) {
-            const long long c0 = trace ? clock64() : 0;
-            mbar_wait(&afull[as], aph, ab);
-            if (kb == 0) { IE_TRACE(2, k); t_first = trace ? clock64() : 0; }
-            else if (trace) wa += clock64() - c0;
-          }
-          if (jw == 0) {
-            const long long c0 = trace ? clock64() : 0;
-            mbar_wait(&wfull[ws], wph, ab);
-            if (trace) ww += clock64() - c0;
-          }
+          const long long c0 = trace ? clock64() : 0;
+          mbar_wait(&full[st], ph, ab);
+          if (kb == 0) { IE_TRACE(2, k); t_first = trace ? clock64() : 0; }
+          else if (trace) wa += clock64() - c0;
           tc_fence_after();
-          const uint64_t da = umma_desc_sw128(a_base + (as * kLGA + ja) * a_bytes);
-          const uint64_t db = umma_desc_sw128(w_base + (ws * kLGW + jw) * w_bytes);
+          const uint64_t da = umma_desc_sw128(ring_base + st * stage_bytes);
+          const uint64_t db = umma_desc_sw128(ring_base + st * stage_bytes + a_bytes);
 #pragma unroll
           for (int q = 0; q < 4; ++q) umma_bf16_pair(tmem_d, da + 2 * q, db + 2 * q, idesc, (kb | q) != 0);
-          const bool last = (kb == nkt - 1);
-          if (ja == kLGA - 1 || last) {
-            umma_commit_pair_mc(&aempty[as], 0x3);
-            if (++as == kLAStages) { as = 0; aph ^= 1; }
-          }
-          if (jw == kLGW - 1 || last) {
-            umma_commit_pair_mc(&wempty[ws], 0x3);
-            if (++ws == kLWStages) { ws = 0; wph ^= 1; }
-          }
+          umma_commit_pair_mc(&empty[st], 0x3);
+          if (++st == kLStages) { st = 0; ph ^= 1; }
         }
         umma_commit_pair_mc(&tfull[slot], 0x3);
         IE_TRACE(3, k);
-        IE_TRACE_VAL(8, k, wa);
-        IE_TRACE_VAL(9, k, ww);
+        IE_TRACE_VAL(8, k, wa);                                        // SM cycles waiting for operand stages
+        IE_TRACE_VAL(9, k, 0);
         IE_TRACE_VAL(10, k, trace ? clock64() - t_first : 0);
       }
     }
@@ -286,7 +260,6 @@ lstm_layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constan
     const int q = e & 3;
     const int cq = e >> 2;  // which 64 of the tile's 256 columns (4 chunks of 16 = 16 hidden units per thread)
     const int row = static_cast<int>(crank) * 128 + q * 32 + lane;
-    const bool pooled = a.pool_sum != nullptr;
     const long long lo_off = a.segs > 1 ? a.kh_pad : 0;
     int k = 0;
     for (long long n = pair; n < total; n += P, ++k) {
@@ -297,7 +270,7 @@ lstm_layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constan
       const int slot = k & 1;
       const int brow = g * 256 + row;
       const int unit0 = j * 64 + cq * 16;
-      const int len = pooled ? a.lengths[brow] : 1;
+      const int len = POOL ? a.lengths[brow] : 1;
       const long long grow = TOK ? static_cast<long long>(__ldg(a.tok + static_cast<long long>(tg) * b_pad + brow))
                                  : static_cast<long long>(t) * b_pad + brow;  // TOK: per-token projection table
       float* cp = a.cstate + static_cast<long long>(brow) * a.out_pad + unit0;
@@ -326,6 +299,15 @@ lstm_layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constan
 #pragma unroll
       for (int ch = 0; ch < kCh; ++ch)
         cr[ch] = (tg == 0) ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldcg(reinterpret_cast<const float4*>(cp) + ch);
+      // last layer: the running max travels like c (L2, loaded before the accumulator is ready); the sum is an L2 reduction
+      [[maybe_unused]] float4 pm[POOL ? kCh : 1];
+      [[maybe_unused]] const long long po = static_cast<long long>(brow) * a.out_pad + unit0;
+      if constexpr (POOL) {
+        if (tg > 0 && tg < len) {
+#pragma unroll
+          for (int ch = 0; ch < kCh; ++ch) pm[ch] = __ldcg(reinterpret_cast<const float4*>(a.pool_max + po) + ch);
+        }
+      }
       if (threadIdx.x == 128) IE_TRACE(7, k);
       mbar_wait(&tfull[slot], static_cast<uint32_t>((k >> 1) & 1), ab);
       tc_fence_after();
@@ -354,9 +336,7 @@ lstm_layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constan
           float4* rp = reinterpret_cast<float4*>(a.raw + (static_cast<long long>(brow) * a.T_total + tg) * a.raw_ld + unit0 + ch * 4);
           *rp = make_float4(hn[0], hn[1], hn[2], hn[3]);
         }
-        if (pooled)
-          pool_accumulate4(a.pool_sum, a.pool_max, a.pool_last, static_cast<long long>(brow) * a.out_pad + unit0 + ch * 4, hn,
-                           tg, len);
+        if constexpr (POOL) pool_accumulate4(a.pool_sum, a.pool_max, a.pool_last, po + ch * 4, hn, pm[ch], tg, len);
       }
       // publish (step t, batch g): accumulator slot drained, h_t / c_t / pooling state visible
       if (threadIdx.x == 128) IE_TRACE(5, k);
@@ -390,13 +370,12 @@ lstm_layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constan
 }
 
 size_t layer_smem_bytes() {
-  return 1024 + static_cast<size_t>(kLAStages) * kLGA * 128 * 64 * 2 + static_cast<size_t>(kLWStages) * kLGW * kLHalfRows * 64 * 2 +
-         (2 * kLAStages + 2 * kLWStages + 4) * 8 + 32;
+  return 1024 + static_cast<size_t>(kLStages) * (128 * 64 * 2 + kLHalfRows * 64 * 2) + (2 * kLStages + 4) * 8 + 32;
 }
 
-template <bool TOK, bool GXBF>
+template <bool TOK, bool GXBF, bool POOL>
 cudaError_t launch_layer_t(const LstmLayerArgs& a, int pairs, int tiles, cudaStream_t stream) {
-  auto kfn = lstm_layer_kernel<TOK, GXBF>;
+  auto kfn = lstm_layer_kernel<TOK, GXBF, POOL>;
   const size_t smem = layer_smem_bytes();
   // function attributes are per device: set on every launch (cheap), never cached in a process-wide flag
   cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
@@ -446,8 +425,12 @@ cudaError_t launch_lstm_layer(const LstmLayerArgs& a, cudaStream_t stream) {
   const int pairs = lstm_layer_pairs(a);
   if (pairs < 1) return cudaErrorInvalidValue;
   const bool tok = a.tok != nullptr;  // layer 0 reading its input projection from the per-token table
-  if (a.gx_bf16) return tok ? launch_layer_t<true, true>(a, pairs, tiles, stream) : launch_layer_t<false, true>(a, pairs, tiles, stream);
-  return tok ? launch_layer_t<true, false>(a, pairs, tiles, stream) : launch_layer_t<false, false>(a, pairs, tiles, stream);
+  const bool pool = a.pool_sum != nullptr;
+#define IE_LAYER(T_, G_)                                                                                  \
+  (pool ? launch_layer_t<T_, G_, true>(a, pairs, tiles, stream) : launch_layer_t<T_, G_, false>(a, pairs, tiles, stream))
+  if (a.gx_bf16) return tok ? IE_LAYER(true, true) : IE_LAYER(false, true);
+  return tok ? IE_LAYER(true, false) : IE_LAYER(false, false);
+#undef IE_LAYER
 }
 
 }  // namespace ie

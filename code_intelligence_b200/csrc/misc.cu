@@ -101,10 +101,9 @@ __global__ void pool_finalize_kernel(const float* __restrict__ pool_sum, const f
   const float inv = 1.0f / static_cast<float>(lengths[b]);
   const long long po = static_cast<long long>(b) * out_pad;
   float* o = out + static_cast<long long>(b) * 3 * e;
-  const uint32_t* pmax = reinterpret_cast<const uint32_t*>(pool_max);  // order-preserving encoding (lstm_common.cuh)
   for (int i = threadIdx.x; i < e; i += blockDim.x) {
     o[i] = pool_sum[po + i] * inv;
-    o[e + i] = dec_max(pmax[po + i]);
+    o[e + i] = pool_max[po + i];
     o[2 * e + i] = pool_last[po + i];
   }
 }

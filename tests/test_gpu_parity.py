@@ -21,6 +21,16 @@ pytestmark = pytest.mark.gpu
 COS_MIN = 1 - 1e-4
 REL_L2_MAX = 4e-3          # torch-default init (|h| ~ 0.01)
 REL_L2_MAX_SCALED = 1e-2   # "trained-like" weight sets (LSTM weights x2..x3, |h| ~ 0.1): bf16 rounding of h amplifies
+CC_MIN_FULL = 0.985        # centred cosine at 512..2048 steps under torch-default init: the per-issue signal after
+                           # removing the batch mean is ~1 % of the vector, so the same rel-L2 (8e-4) reads 0.990-0.992
+                           # here (measured, profiles/); the permuted-rows negative control scores < 0.9
+
+
+def _usable_cpus():
+    """Affinity mask capped by the cgroup CPU quota: on the GPU boxes os.cpu_count() is far above what the container may
+    use, and an oversubscribed OpenMP pool makes the CPU oracle orders of magnitude slower (tiny LSTM, 20 000 steps)."""
+    import bench
+    return bench.usable_cpus()
 
 
 def _pad(docs, T=None, pad=1):
@@ -45,7 +55,7 @@ def _assert_parity(got, want, cc_min=0.99, rel_l2_max=REL_L2_MAX):
 def r4():
     """Reference-deployed shape (L=4, E=800, H=2400, V=60000), seed-1234 random init, on the GPU + its oracle."""
     from code_intelligence_b200 import IssueEncoder
-    torch.set_num_threads(os.cpu_count())
+    torch.set_num_threads(_usable_cpus())
     ref = R.make_encoder(1234)
     emb, layers = ref.export_weights()
     enc = IssueEncoder().load_weights(emb, layers)
@@ -95,7 +105,7 @@ def test_golden_small(golden_dir, name):
     enc.close()
 
 
-@pytest.mark.parametrize("name,cc", [("encoder_r4.npz", 0.99), ("encoder_r4_varlen.npz", 0.999)])
+@pytest.mark.parametrize("name,cc", [("encoder_r4.npz", 0.985), ("encoder_r4_varlen.npz", 0.999)])
 def test_golden_r4(golden_dir, r4, name, cc):
     """encoder_r4.npz is BASELINE.json configs[0] (32 issues, seq_len 128) pushed through the GPU path."""
     enc, _ = r4
@@ -245,7 +255,7 @@ def test_golden_r4_bench_shape_all_rows(golden_dir, r4):
     enc, _ = r4
     ids, lengths, want = _golden_full(golden_dir, "encoder_r4_b256_t512.npz")
     got = enc.encode_ids(ids, lengths)
-    m = _assert_parity(got, want, cc_min=0.99)
+    m = _assert_parity(got, want, cc_min=CC_MIN_FULL)
     print("r4 256x512 single batch", m)
     neg = R.parity_metrics(got, np.roll(want, 1, axis=0))
     assert neg["rel_l2"] > 2 * REL_L2_MAX and neg["min_centred_cosine"] < 0.9
@@ -266,7 +276,7 @@ def test_golden_r4_long_buckets(golden_dir, r4, name, T):
     ids, lengths, want = _golden_full(golden_dir, name)
     assert ids.shape[1] == T
     got = enc.encode_ids(ids, lengths)
-    m = _assert_parity(got, want, cc_min=0.99)
+    m = _assert_parity(got, want, cc_min=CC_MIN_FULL)
     print(name, m)
     rep = np.concatenate([ids] * 17)[:513]            # 513 rows: three 256-row batches in one launch
     got3 = enc.encode_ids(rep, np.concatenate([lengths] * 17)[:513])
@@ -414,7 +424,10 @@ def test_very_long_issue_is_chunked(monkeypatch):
     T = 20000
     doc = R.synthetic_ids(1, T, seed=6, vocab_sz=cfg[3])[0]
     got = enc.encode_ids(doc[None, :])
+    nthreads = torch.get_num_threads()
+    torch.set_num_threads(min(4, nthreads))     # 20 000 tiny steps: thread-pool barriers would dominate
     want = R.encode_single(ref, doc)
+    torch.set_num_threads(nthreads)
     _assert_parity(got, want, rel_l2_max=REL_L2_MAX_SCALED)
     short = enc.encode_ids(doc[None, :], np.array([5000], dtype=np.int32))
     np.testing.assert_array_equal(short, enc.encode_ids(doc[None, :5000]))

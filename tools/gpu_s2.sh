@@ -4,8 +4,8 @@ set -u
 mkdir -p gpurun_out
 O=gpurun_out; TAG=${1:-s2}
 echo "== pytest -m gpu"
-timeout 1500 python -m pytest tests -m gpu -q -s > $O/pytest_gpu_$TAG.log 2>&1
-echo "rc=$?"; grep -E "passed|failed|error" $O/pytest_gpu_$TAG.log | tail -5; grep -E "^FAILED|^ERROR" $O/pytest_gpu_$TAG.log | head -20
+timeout 1500 python -m pytest tests -m gpu -v -s --timeout 400 --timeout-method=thread > $O/pytest_gpu_$TAG.log 2>&1
+echo "rc=$?"; grep -E "passed|failed|error" $O/pytest_gpu_$TAG.log | tail -5; grep -E "FAILED|ERROR|Timeout" $O/pytest_gpu_$TAG.log | head -20
 grep -E "^(r4|encoder_|n3|fp32|varlen|full-size)" $O/pytest_gpu_$TAG.log | cut -c1-400
 echo "== bench"
 timeout 600 python bench.py > $O/bench_$TAG.json 2> $O/bench_$TAG.err; echo "rc=$?"; tail -3 $O/bench_$TAG.err
