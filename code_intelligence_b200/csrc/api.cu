@@ -104,6 +104,8 @@ struct ie_encoder {
   int use_persistent = 1;  // cooperative persistent kernel; 0 (IE_SEQ=0 or not co-resident): per-timestep fallback
   int persist_checked = 0;
   int cooperative = 1;     // launch attribute (IE_COOP=0: plain launch, co-residency by the occupancy check only)
+  int use_mc = 0;          // IE_MC=1: sibling CTA pairs share h tiles by TMA multicast (clusters of four)
+  int mc_pairs = 0;        // pairs co-resident in clusters of four
   int batches = 5;         // batches of 256 rows one launch takes (IE_BATCHES, <= kMaxBatches)
   int max_batch = 1280;
   // layer 0's input projection W_ih0 . Emb[id] + b depends on the token id alone: tabulated once per weight set
@@ -321,6 +323,14 @@ int check_persistent(ie_encoder* h, cudaStream_t s) {
     q.num_sms = h->num_sms; q.check_only = 1;
     if (ie::launch_lstm_layer(q, s) != cudaSuccess) h->use_persistent = 0;
   }
+  if (h->use_mc) {
+    ie::LstmLayerArgs q{};
+    const Layer& L = h->layers[0];
+    q.T = 1; q.ng = 1; q.u = L.u; q.n_cta = L.n_cta; q.out_pad = L.out_pad; q.kh_pad = L.kh_pad; q.segs = 1;
+    q.num_sms = h->num_sms; q.check_only = 1; q.mc = 1; q.gx_bf16 = 1;
+    if (ie::launch_lstm_layer(q, s) == cudaSuccess) h->mc_pairs = ie::lstm_layer_max_pairs() & ~1;
+    if (h->mc_pairs < 2) h->use_mc = 0;
+  }
   cudaGetLastError();
   h->persist_checked = 1;
   return IE_OK;
@@ -421,6 +431,10 @@ int run_encoder(ie_encoder* h, const int64_t* ids, const int32_t* lengths, int B
                                h->y_ld, 64, 128));
       CK(ie::make_tmap_bf16_2d(&tm_w, L.w_hh.p, static_cast<uint64_t>(ring_mul) * L.kh_pad, 4ull * L.out_pad,
                                static_cast<uint64_t>(ring_mul) * L.kh_pad, 64, 128));
+      CUtensorMap tm_h64 = tm_h;
+      if (h->use_mc)
+        CK(ie::make_tmap_bf16_2d(&tm_h64, ybuf, static_cast<uint64_t>(ring_mul) * L.kh_pad,
+                                 static_cast<uint64_t>(crow + b_pad), h->y_ld, 64, 64));
       // slot 0 of the ring = this layer's h at the end of the previous chunk (zeros before the first)
       CK(cudaMemcpyAsync(ybuf, carry, slot_bytes, cudaMemcpyDeviceToDevice, s));
       if (!from_table) {
@@ -441,7 +455,7 @@ int run_encoder(ie_encoder* h, const int64_t* ids, const int32_t* lengths, int B
       if (persistent) {
         CK(cudaMemsetAsync(h->step_done.p, 0, static_cast<size_t>(Tc) * ng * sizeof(unsigned), s));
         ie::LstmLayerArgs q{};
-        q.tm_h = tm_h; q.tm_w = tm_w;
+        q.tm_h = tm_h; q.tm_w = tm_w; q.tm_h64 = tm_h64; q.mc = h->use_mc; q.mc_pairs = h->mc_pairs;
         q.gx = from_table ? h->proj.p : h->gx.p;
         q.tok = from_table ? h->tok.as<int>() : nullptr;
         q.c = cstate; q.y = ybuf;
@@ -594,6 +608,7 @@ int ie_encoder_create(const ie_config* cfg, ie_encoder** out) {
   // development knobs; none is needed in production
   if (const char* v = getenv("IE_SEQ")) h->use_persistent = atoi(v);
   if (const char* v = getenv("IE_COOP")) h->cooperative = atoi(v);
+  if (const char* v = getenv("IE_MC")) h->use_mc = atoi(v);
   if (const char* v = getenv("IE_EMB_PROJ")) h->use_proj = atoi(v);
   if (const char* v = getenv("IE_GX_BF16")) { if (h->segs == 1) h->gx_bf16 = atoi(v); }
   if (const char* v = getenv("IE_FAST_MATH")) { if (h->segs == 1) h->gate_mode = atoi(v) ? 2 : 1; }

@@ -393,7 +393,7 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           fence_proxy_async_smem();                           // generic-proxy writes -> visible to the TMA store
           named_bar_sync(2, 128);
           if (threadIdx.x == 128) {
-            tma_store_2d(&tmD, buf, n_blk * bn + c0, row0);   // clipped to [m_store, n_store] by the tensor map
+            tma_store_2d_hint(&tmD, buf, n_blk * bn + c0, row0, kEvictFirst);   // clipped by the tensor map
             bulk_commit_group();
           }
         }
@@ -510,7 +510,12 @@ cudaError_t launch_gemm_bf16(const GemmArgs& g, cudaStream_t stream) {
     const int num_n_blocks = g.n_pad / g.bn;
     const int num_k_blocks = g.k_pad / kBlockK;
     const int grid = 2 * (sms0 / 2);
-    int panel = sms0 / 4;
+    // m-blocks per panel (tile order: m fastest inside a panel, then n).  The CTA pairs running together then share
+    // ~panel A blocks and ~num_pairs/panel B tiles: with 8 the working set is ~10 MB of A + ~12 MB of B, far inside the
+    // L2 even next to the output stream (round 1's 37 kept 93 MB live: ncu showed 40 GB of DRAM reads for 3.3 GB of
+    // operands in a 2400 x 9600 projection -- profiles/README.md)
+    int panel = 8;
+    if (const char* v = getenv("IE_GEMM_PANEL")) panel = atoi(v);
     if (panel < 1) panel = 1;
 #define IE_LAUNCH_PAIR(OUT, ACT)                                                                                  \
   do {                                                                                                            \

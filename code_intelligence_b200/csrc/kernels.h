@@ -63,6 +63,9 @@ cudaError_t launch_lstm_step(const LstmStepArgs& a, cudaStream_t stream);
 constexpr int kMaxBatches = 8;
 struct LstmLayerArgs {
   CUtensorMap tm_h, tm_w;  // as LstmStepArgs
+  CUtensorMap tm_h64;      // same tensor as tm_h with box {64, 64}: the quarter tile one CTA multicasts (mc != 0)
+  int mc;                  // 1: clusters of two CTA pairs share every h tile by TMA multicast (needs an even number of tiles)
+  int mc_pairs;            // CTA pairs that can be co-resident in clusters of four (lstm_layer_max_pairs() of a check_only query)
   const void* gx;
   const int* tok;
   float* c;
@@ -88,6 +91,7 @@ struct LstmLayerArgs {
 };
 cudaError_t launch_lstm_layer(const LstmLayerArgs& a, cudaStream_t stream);
 int lstm_layer_pairs(const LstmLayerArgs& a);  // CTA pairs the launch will use
+int lstm_layer_max_pairs();                    // result of the last check_only query on this thread
 
 // ---- small memory-bound kernels (misc.cu) --------------------------------------------------------
 // ids [B, T] int64 (batch-first, right padded) -> x0 [(T*b_pad), ldx] bf16, time-major rows t*b_pad + b

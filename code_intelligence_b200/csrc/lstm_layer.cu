@@ -83,11 +83,18 @@ struct KArgs {
 };
 
 // TOK: Gx rows are rows of the per-token input-projection table; GXBF: Gx / table stored as fp16 (f32 otherwise);
-// POOL: last layer -- the masked concat-pool accumulators ride the epilogue
-template <bool TOK, bool GXBF, bool POOL>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kLThreads, 1)
+// POOL: last layer -- the masked concat-pool accumulators ride the epilogue;
+// MC: clusters of FOUR CTAs = two sibling pairs (2q, 2q+1).  Sibling pairs always hold items n, n+1 = the same
+//     (timestep, batch) and adjacent column tiles (tiles, C and P even), i.e. they need the SAME h tile: each CTA loads a
+//     quarter of it and multicasts it to its counterpart in the sibling pair, so an h tile leaves the L2 once per two
+//     items.  The kernel is bound by L2 -> SM bytes (both operands stream from L2 at ~9.5 TB/s chip-wide, the practical
+//     LTS limit -- profiles/README.md); this removes a quarter of them.  A stage is refilled only when BOTH pairs have
+//     consumed it (empty barriers count two commits, each multicast to all four CTAs).
+// Cluster dimensions come from the launch (cudaLaunchAttributeClusterDimension: 2, or 4 with MC).
+template <bool TOK, bool GXBF, bool POOL, bool MC>
+__global__ void __launch_bounds__(kLThreads, 1)
 lstm_layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ CUtensorMap tm_w,
-                  const __grid_constant__ KArgs a) {
+                  const __grid_constant__ CUtensorMap tm_h64, const __grid_constant__ KArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t rawaddr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (rawaddr & 1023u)) & 1023u);
@@ -119,7 +126,12 @@ lstm_layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constan
     trace[(static_cast<long long>(blockIdx.x) * a.trace_items + (kk)) * 12 + (slot)] = static_cast<long long>(_g); } } while (0)
 #define IE_TRACE_VAL(slot, kk, v) do { if (trace && (kk) < a.trace_items) \
     trace[(static_cast<long long>(blockIdx.x) * a.trace_items + (kk)) * 12 + (slot)] = (v); } while (0)
-  const uint32_t crank = cluster_ctarank();
+  const uint32_t crank4 = cluster_ctarank();       // rank in the cluster (0..1, or 0..3 with MC)
+  const uint32_t crank = crank4 & 1u;              // rank in the CTA pair: 0 = leader
+  const uint32_t cpair = crank4 >> 1;              // which pair of the cluster (MC only; 0 otherwise)
+  const uint32_t leader = crank4 & ~1u;            // cluster rank of this pair's leader
+  const uint16_t pmask = static_cast<uint16_t>(0x3u << (2 * cpair));   // the CTAs of this pair
+  const uint16_t emask = MC ? 0xF : pmask;         // who must see a stage release
   const int pair = blockIdx.x >> 1;
   const int P = static_cast<int>(gridDim.x >> 1);
   const int tiles = a.tiles, ng = a.ng;
@@ -132,6 +144,7 @@ lstm_layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constan
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_h);
     tma_prefetch_desc(&tm_w);
+    if (MC) tma_prefetch_desc(&tm_h64);
     if (a.diag != nullptr && blockIdx.x == 0) {  // SM clock of this launch = d(clock64) / d(globaltimer)
       unsigned long long g;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
@@ -142,7 +155,7 @@ lstm_layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constan
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kLStages; ++s) {
       mbar_init(&full[s], 4);
-      mbar_init(&empty[s], 1);
+      mbar_init(&empty[s], MC ? 2 : 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull[s], 1);
@@ -175,10 +188,17 @@ lstm_layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constan
         for (int kb = 0; kb < nkt; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1, ab);
           if (crank == 0) mbar_arrive_expect_tx(&full[stage], 2 * a_bytes);
-          else mbar_arrive_remote(&full[stage], 0);
+          else mbar_arrive_remote(&full[stage], leader);
           const int seg = kb / a.nkb, r = kb - seg * a.nkb;            // split-bf16: [h_hi | h_lo | h_hi]
-          tma_load_2d_pair(ring + stage * stage_bytes, &tm_h, &full[stage], (seg == 1 ? a.kh_pad : 0) + r * 64, row0,
-                           kEvictNormal);
+          if constexpr (MC) {
+            // quarter tile: rows [64 * cpair, +64) of this CTA's 128 rows, to this CTA and its counterpart in the sibling pair
+            tma_load_2d_pair_mc(ring + stage * stage_bytes + cpair * (a_bytes / 2), &tm_h64, &full[stage],
+                                (seg == 1 ? a.kh_pad : 0) + r * 64, row0 + static_cast<int>(cpair) * 64,
+                                static_cast<uint16_t>(0x5u << crank), kEvictNormal);
+          } else {
+            tma_load_2d_pair(ring + stage * stage_bytes, &tm_h, &full[stage], (seg == 1 ? a.kh_pad : 0) + r * 64, row0,
+                             kEvictNormal);
+          }
           if (++stage == kLStages) { stage = 0; phase ^= 1; }
         }
         IE_TRACE(1, k);
@@ -208,7 +228,7 @@ lstm_layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constan
         for (int kb = 0; kb < nkt; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1, ab);
           if (crank == 0) mbar_arrive_expect_tx(&full[stage], 2 * w_bytes);
-          else mbar_arrive_remote(&full[stage], 0);
+          else mbar_arrive_remote(&full[stage], leader);
           const int seg = kb / a.nkb, r = kb - seg * a.nkb;            // split-bf16: [W_hi | W_hi | W_lo]
           tma_load_2d_pair(ring + stage * stage_bytes + a_bytes, &tm_w, &full[stage], (seg == 2 ? a.kh_pad : 0) + r * 64,
                            wrow0, kEvictLast);
@@ -243,10 +263,10 @@ lstm_layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constan
           const uint64_t db = umma_desc_sw128(ring_base + st * stage_bytes + a_bytes);
 #pragma unroll
           for (int q = 0; q < 4; ++q) umma_bf16_pair(tmem_d, da + 2 * q, db + 2 * q, idesc, (kb | q) != 0);
-          umma_commit_pair_mc(&empty[st], 0x3);
+          umma_commit_pair_mc(&empty[st], emask);
           if (++st == kLStages) { st = 0; ph ^= 1; }
         }
-        umma_commit_pair_mc(&tfull[slot], 0x3);
+        umma_commit_pair_mc(&tfull[slot], pmask);
         IE_TRACE(3, k);
         IE_TRACE_VAL(8, k, wa);                                        // SM cycles waiting for operand stages
         IE_TRACE_VAL(9, k, 0);
@@ -343,7 +363,7 @@ lstm_layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constan
       tc_fence_before();
       named_bar_sync(1, 512);
       if (threadIdx.x == 128) {
-        mbar_arrive_remote(&tempty[slot], 0);
+        mbar_arrive_remote(&tempty[slot], leader);
         __threadfence();
         // fault injection for the abort-protocol test (IE_DEBUG_FAULT): item (t=1, g=0, j=0) is never published
         if (!(a.fault && n == C)) red_relaxed_add(a.step_done + t * ng + g, 1u);
@@ -369,26 +389,46 @@ lstm_layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constan
 #undef IE_TRACE_VAL
 }
 
+thread_local int g_last_max_pairs = 0;   // result of the last check_only query on this thread
+
 size_t layer_smem_bytes() {
   return 1024 + static_cast<size_t>(kLStages) * (128 * 64 * 2 + kLHalfRows * 64 * 2) + (2 * kLStages + 4) * 8 + 32;
 }
 
-template <bool TOK, bool GXBF, bool POOL>
+template <bool TOK, bool GXBF, bool POOL, bool MC>
 cudaError_t launch_layer_t(const LstmLayerArgs& a, int pairs, int tiles, cudaStream_t stream) {
-  auto kfn = lstm_layer_kernel<TOK, GXBF, POOL>;
+  auto kfn = lstm_layer_kernel<TOK, GXBF, POOL, MC>;
   const size_t smem = layer_smem_bytes();
   // function attributes are per device: set on every launch (cheap), never cached in a process-wide flag
   cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return e;
+  if (MC) {
+    e = cudaFuncSetAttribute(kfn, cudaFuncAttributeNonPortableClusterSizeAllowed, 0);
+    if (e != cudaSuccess) return e;
+  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2 * (a.check_only ? a.num_sms / 2 : pairs));
   cfg.blockDim = dim3(kLThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = MC ? 4 : 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeCooperative;
+  attr[1].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
   if (a.check_only) {
+    // how many CTA pairs can be co-resident with this cluster shape (returned through a.check_only's contract: the
+    // caller reads lstm_layer_max_pairs())
+    if (MC) cfg.gridDim = dim3(4 * (a.num_sms / 4));
     int max_clusters = 0;
     e = cudaOccupancyMaxActiveClusters(&max_clusters, kfn, &cfg);
     if (e != cudaSuccess) return e;
+    g_last_max_pairs = max_clusters * (MC ? 2 : 1);
+    if (MC) return max_clusters >= 1 ? cudaSuccess : cudaErrorCooperativeLaunchTooLarge;
     return max_clusters >= a.num_sms / 2 ? cudaSuccess : cudaErrorCooperativeLaunchTooLarge;
   }
   KArgs k{};
@@ -400,34 +440,42 @@ cudaError_t launch_layer_t(const LstmLayerArgs& a, int pairs, int tiles, cudaStr
   k.T = a.T; k.t0 = a.t0; k.T_total = a.T_total; k.ng = a.ng; k.tiles = tiles; k.out_pad = a.out_pad;
   k.nkb = a.kh_pad / 64; k.segs = a.segs; k.kh_pad = a.kh_pad; k.gate_mode = a.gate_mode;
   k.trace_items = a.trace_items; k.fault = a.fault;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeCooperative;
-  attr[0].val.cooperative = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = a.cooperative ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, kfn, a.tm_h, a.tm_w, k);
+  cfg.numAttrs = a.cooperative ? 2 : 1;
+  return cudaLaunchKernelEx(&cfg, kfn, a.tm_h, a.tm_w, a.tm_h64, k);
 }
 
 }  // namespace
 
+int lstm_layer_max_pairs() { return g_last_max_pairs; }
+
+// multicast needs sibling pairs to hold items of the same (timestep, batch): tiles (hence C and the item total) even
+bool lstm_layer_mc_ok(const LstmLayerArgs& a) {
+  return a.mc != 0 && a.gx_bf16 && a.pool_sum == nullptr && a.segs == 1 && (a.n_cta / 2) % 2 == 0 && a.mc_pairs >= 2;
+}
+
 int lstm_layer_pairs(const LstmLayerArgs& a) {
   const long long total = static_cast<long long>(a.T) * a.ng * (a.n_cta / 2);
-  long long pairs = a.num_sms / 2;
+  long long pairs = lstm_layer_mc_ok(a) ? a.mc_pairs : a.num_sms / 2;
   if (pairs > total) pairs = total;
+  if (lstm_layer_mc_ok(a)) pairs &= ~1ll;
   return static_cast<int>(pairs);
 }
 
-// a.check_only: only verify that a full grid can be co-resident.  Requires u == 32 per CTA (64 units per pair tile).
+// a.check_only: only query co-residency (lstm_layer_max_pairs()).  Requires u == 32 per CTA (64 units per pair tile).
 cudaError_t launch_lstm_layer(const LstmLayerArgs& a, cudaStream_t stream) {
   if (a.u != 32 || a.n_cta % 2 || a.kh_pad % 64 || a.ng < 1 || a.ng > kMaxBatches || a.T < 1 || (a.segs != 1 && a.segs != 3))
     return cudaErrorInvalidValue;
   const int tiles = a.n_cta / 2;
+  if (a.check_only && a.mc) return launch_layer_t<false, true, false, true>(a, 0, tiles, stream);
   const int pairs = lstm_layer_pairs(a);
   if (pairs < 1) return cudaErrorInvalidValue;
   const bool tok = a.tok != nullptr;  // layer 0 reading its input projection from the per-token table
   const bool pool = a.pool_sum != nullptr;
+  if (!a.check_only && lstm_layer_mc_ok(a))
+    return tok ? launch_layer_t<true, true, false, true>(a, pairs, tiles, stream)
+               : launch_layer_t<false, true, false, true>(a, pairs, tiles, stream);
 #define IE_LAYER(T_, G_)                                                                                  \
-  (pool ? launch_layer_t<T_, G_, true>(a, pairs, tiles, stream) : launch_layer_t<T_, G_, false>(a, pairs, tiles, stream))
+  (pool ? launch_layer_t<T_, G_, true, false>(a, pairs, tiles, stream) : launch_layer_t<T_, G_, false, false>(a, pairs, tiles, stream))
   if (a.gx_bf16) return tok ? IE_LAYER(true, true) : IE_LAYER(false, true);
   return tok ? IE_LAYER(true, false) : IE_LAYER(false, false);
 #undef IE_LAYER

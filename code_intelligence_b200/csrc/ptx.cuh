@@ -141,6 +141,13 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* s
                ::"l"(m), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
                : "memory");
 }
+// same with an L2 cache-policy hint (evict-first: an output stream must not displace the operand panels in L2)
+__device__ __forceinline__ void tma_store_2d_hint(const CUtensorMap* m, const void* smem_src, int32_t c0, int32_t c1,
+                                                  uint64_t hint) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;"
+               ::"l"(m), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "l"(hint)
+               : "memory");
+}
 __device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // wait until at most N of this thread's bulk groups still READ their shared-memory source / are incomplete
 template <int N> __device__ __forceinline__ void bulk_wait_group_read() {
@@ -253,6 +260,18 @@ __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorM
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
       " [%0], [%1, {%3, %4}], [%2], %5;"
       ::"r"(smem_u32(smem_dst)), "l"(m), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "l"(hint)
+      : "memory");
+}
+// multicast variant of tma_load_2d_pair: the box lands at the same CTA-relative offset in every CTA of `mask`; with
+// cta_group::2 the complete_tx of each destination goes to the barrier (same offset) of the CTA of ITS pair whose rank has
+// the parity of the CTA `bar` points to -- `bar` is redirected to this pair's leader, so every destination pair's
+// leader is signalled
+__device__ __forceinline__ void tma_load_2d_pair_mc(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int32_t c0,
+                                                    int32_t c1, uint16_t mask, uint64_t hint) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      ".L2::cache_hint [%0], [%1, {%4, %5}], [%2], %3, %6;"
+      ::"r"(smem_u32(smem_dst)), "l"(m), "r"(smem_u32(bar) & kPeerBitMask), "h"(mask), "r"(c0), "r"(c1), "l"(hint)
       : "memory");
 }
 // plain arrive on the barrier at the same smem offset in CTA `cta` of the cluster

@@ -201,7 +201,7 @@ def test_edge_cases_and_errors(r4):
     assert np.isfinite(enc.encode_ids(ids[:2], lengths[:2])).all()            # handle still usable
 
 
-KNOBS = ("IE_SEQ", "IE_COOP", "IE_EMB_PROJ", "IE_GX_BF16", "IE_BATCHES", "IE_CHUNK_T", "IE_FAST_MATH",
+KNOBS = ("IE_SEQ", "IE_COOP", "IE_EMB_PROJ", "IE_GX_BF16", "IE_BATCHES", "IE_CHUNK_T", "IE_FAST_MATH", "IE_MC",
          "IE_SPIN_LIMIT_MS", "IE_DEBUG_FAULT")
 
 
@@ -220,6 +220,7 @@ def _make(cfg, weights, monkeypatch, env=None, flags=0):
 
 @pytest.mark.parametrize("knobs", [{"IE_SEQ": 0}, {"IE_EMB_PROJ": 0}, {"IE_EMB_PROJ": 0, "IE_SEQ": 0}, {"IE_BATCHES": 3},
                                    {"IE_BATCHES": 8}, {"IE_CHUNK_T": 5}, {"IE_CHUNK_T": 1, "IE_EMB_PROJ": 0}, {"IE_COOP": 0},
+                                   {"IE_MC": 1}, {"IE_MC": 0}, {"IE_MC": 1, "IE_BATCHES": 4, "IE_CHUNK_T": 7},
                                    {"IE_GX_BF16": 0, "_base": {"IE_GX_BF16": 0, "IE_SEQ": 0, "IE_CHUNK_T": 3}}])
 def test_every_path_gives_identical_bits(knobs, monkeypatch):
     """One persistent kernel (csrc/lstm_layer.cu) + one fallback (csrc/lstm.cu, IE_SEQ=0) share the cell arithmetic of
