@@ -323,7 +323,7 @@ def main():
         a[a == 1] = 0
         a[:, 0] = 2
         return list(a)
-    docs_warm = make_docs(world * W * B, rng)
+    docs_warm = make_docs(n_total, rng)      # same shape as the timed call: buffers of the right size exist afterwards
     docs = make_docs(n_total, rng)
     local_fn = lambda d: bulk.encode_sorted_batches_device(d, enc, min_batches_rule=False, to_host=False)
     bulk.encode_bulk_distributed(docs_warm, local_fn, device=dev)

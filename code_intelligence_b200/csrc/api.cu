@@ -793,8 +793,11 @@ int ie_mlp_create(int32_t n_layers, const int32_t* dims, int32_t device, ie_mlp*
   for (int l = 0; l < n_layers; ++l) {
     ie_mlp::L& L = m->layers[l];
     L.k_pad = static_cast<int>(round_up(dims[l], 64));
+    // N tile: a tcgen05.mma costs about the same whatever its N (profiles/README.md), so wide layers use the full N = 256
+    // (a 600-wide hidden layer is padded to 768 = 3 tiles: 123 instead of 185 instruction slots per 128-row tile for the
+    // (1600, 600, 600, 256) head) and narrow ones a single tile
     const int n16 = static_cast<int>(round_up(dims[l + 1], 16));
-    L.bn = n16 >= 128 ? 128 : n16;
+    L.bn = n16 >= 256 ? 256 : n16;
     L.n_pad = static_cast<int>(round_up(dims[l + 1], L.bn));
     ld = std::max<long long>(ld, round_up(std::max(L.n_pad, L.k_pad), 64));
   }

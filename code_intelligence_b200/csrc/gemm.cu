@@ -493,7 +493,10 @@ cudaError_t launch_gemm_bf16(const GemmArgs& g, cudaStream_t stream) {
     if (e != cudaSuccess) return e;
     int stages = 8;
     const char* tma_env = getenv("IE_GEMM_TMA_STORE");            // IE_GEMM_TMA_STORE=0: direct 256-bit stores (A/B runs)
-    const bool tma_store = g.out_bf16 != 0 && !(tma_env && atoi(tma_env) == 0);  // 16-bit outputs: SMEM + TMA stores
+    // 16-bit outputs: SMEM + TMA stores.  The store box is 64 columns wide: N tiles that are not a multiple of 64 would
+    // let a tile's last box cover its neighbour's columns, so those keep the direct stores (unless there is one N tile
+    // and the tensor map clips the box)
+    const bool tma_store = g.out_bf16 != 0 && !(tma_env && atoi(tma_env) == 0) && (g.bn % 64 == 0 || g.n_pad == g.bn);
     auto pair_smem = [&](int st) {
       return 1024 + static_cast<size_t>(st) * (kBlockM * kBlockK * 2 + (g.bn / 2) * kBlockK * 2) +
              (tma_store ? 2 * 128 * 128 : 0) + (2 * st + 4) * 8 + 32;

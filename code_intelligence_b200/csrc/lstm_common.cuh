@@ -94,6 +94,16 @@ __device__ __forceinline__ void pool_accumulate4(float* pool_sum, float* pool_ma
   if (tg == len - 1) __stcg(reinterpret_cast<float4*>(pool_last + po), h4);
 }
 
+// sum / last part only (the persistent kernel writes the running max of two chunks with one 256-bit store)
+__device__ __forceinline__ void pool_sum_last4(float* pool_sum, float* pool_last, long long po, const float (&hn)[4], int tg,
+                                               int len) {
+  if (tg >= len) return;
+  const float4 h4 = make_float4(hn[0], hn[1], hn[2], hn[3]);
+  if (tg == 0) __stcg(reinterpret_cast<float4*>(pool_sum + po), h4);
+  else red_add_v4(pool_sum + po, hn[0], hn[1], hn[2], hn[3]);
+  if (tg == len - 1) __stcg(reinterpret_cast<float4*>(pool_last + po), h4);
+}
+
 // order-preserving u32 encoding of f32 (used by pr_curve.cu to sort scores as integers)
 __device__ __forceinline__ uint32_t enc_max(float x) {
   const uint32_t b = __float_as_uint(x);

@@ -332,6 +332,12 @@ lstm_layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constan
       mbar_wait(&tfull[slot], static_cast<uint32_t>((k >> 1) & 1), ab);
       tc_fence_after();
       if (threadIdx.x == 128) IE_TRACE(4, k);
+      // Results of two chunks (8 units) leave with full-sector 256-bit stores: a thread owns one row, so every store
+      // instruction of a warp touches 32 different rows -- 16-byte c / 8-byte h pieces cost four L2 write transactions
+      // per sector instead of one, and the ~8000 store transactions per item were what the epilogue spent its time on.
+      uint32_t hp[8];        // bf16 h of the thread's 16 units, packed
+      float cbuf[8];         // c of the current chunk pair
+      [[maybe_unused]] float mbuf[8];
 #pragma unroll
       for (int ch = 0; ch < kCh; ++ch) {
         uint32_t r[16];
@@ -350,14 +356,40 @@ lstm_layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constan
         const float cprev[4] = {cr[ch].x, cr[ch].y, cr[ch].z, cr[ch].w};
         float cnew[4], hn[4];
         lstm_cell4(r, gx4, cprev, cnew, hn, a.gate_mode);
-        __stcg(reinterpret_cast<float4*>(cp) + ch, make_float4(cnew[0], cnew[1], cnew[2], cnew[3]));
-        store_h4(yrow + ch * 4, hn, lo_off);
+        const int hb = (ch & 1) * 4;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) cbuf[hb + u] = cnew[u];
+        hp[2 * ch] = pack_bf16x2(hn[0], hn[1]);
+        hp[2 * ch + 1] = pack_bf16x2(hn[2], hn[3]);
+        if (lo_off > 0) {   // split-bf16 mode: the residual h - bf16(h) goes to the lo half of the ring row
+          const float2 fa = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hp[2 * ch]));
+          const float2 fb = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hp[2 * ch + 1]));
+          *reinterpret_cast<uint2*>(yrow + lo_off + ch * 4) =
+              make_uint2(pack_bf16x2(hn[0] - fa.x, hn[1] - fa.y), pack_bf16x2(hn[2] - fb.x, hn[3] - fb.y));
+        }
         if (a.raw != nullptr) {
           float4* rp = reinterpret_cast<float4*>(a.raw + (static_cast<long long>(brow) * a.T_total + tg) * a.raw_ld + unit0 + ch * 4);
           *rp = make_float4(hn[0], hn[1], hn[2], hn[3]);
         }
-        if constexpr (POOL) pool_accumulate4(a.pool_sum, a.pool_max, a.pool_last, po + ch * 4, hn, pm[ch], tg, len);
+        if constexpr (POOL) {
+          pool_sum_last4(a.pool_sum, a.pool_last, po + ch * 4, hn, tg, len);
+          const float mp[4] = {pm[ch].x, pm[ch].y, pm[ch].z, pm[ch].w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) mbuf[hb + u] = (tg == 0) ? hn[u] : fmaxf(mp[u], hn[u]);
+        }
+        if (ch & 1) {
+          st_global_cg_v8(cp + (ch - 1) * 4, __float_as_uint(cbuf[0]), __float_as_uint(cbuf[1]), __float_as_uint(cbuf[2]),
+                          __float_as_uint(cbuf[3]), __float_as_uint(cbuf[4]), __float_as_uint(cbuf[5]),
+                          __float_as_uint(cbuf[6]), __float_as_uint(cbuf[7]));
+          if constexpr (POOL) {
+            if (tg < len)
+              st_global_cg_v8(a.pool_max + po + (ch - 1) * 4, __float_as_uint(mbuf[0]), __float_as_uint(mbuf[1]),
+                              __float_as_uint(mbuf[2]), __float_as_uint(mbuf[3]), __float_as_uint(mbuf[4]),
+                              __float_as_uint(mbuf[5]), __float_as_uint(mbuf[6]), __float_as_uint(mbuf[7]));
+          }
+        }
       }
+      st_global_v8(yrow, hp[0], hp[1], hp[2], hp[3], hp[4], hp[5], hp[6], hp[7]);   // h_t: 16 units = one 32-byte sector
       // publish (step t, batch g): accumulator slot drained, h_t / c_t / pooling state visible
       if (threadIdx.x == 128) IE_TRACE(5, k);
       tc_fence_before();

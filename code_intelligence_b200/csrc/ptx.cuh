@@ -381,6 +381,14 @@ __device__ __forceinline__ void st_global_v8(void* p, uint32_t a, uint32_t b, ui
                : "memory");
 }
 
+// 256-bit store that stays out of L1 (state another SM will read from L2 with ld.global.cg)
+__device__ __forceinline__ void st_global_cg_v8(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e,
+                                                uint32_t f, uint32_t g, uint32_t h) {
+  asm volatile("st.global.cg.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d),
+               "r"(e), "r"(f), "r"(g), "r"(h)
+               : "memory");
+}
+
 // streaming 256-bit read-only load (sm_100): no L1 allocation, evict-first in L2 -- a once-read stream must not
 // displace the L2-resident weights.  (The .L2::evict_first qualifier only exists for the 256-bit forms.)
 __device__ __forceinline__ void ldg_stream8(const float* p, float4& a, float4& b) {
