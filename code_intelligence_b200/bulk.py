@@ -171,12 +171,13 @@ def gather_rows(local, n_total: int, world: int, rank: int, group=None):
 
 
 def encode_bulk_distributed(docs: List[np.ndarray], encode_local: Callable[[List[np.ndarray]], "np.ndarray"],
-                            device: Optional[str] = None, group=None, to_host: bool = True):
+                            device: Optional[str] = None, group=None, to_host=True):
     """Every rank passes the same ``docs`` (the reference's per-repo list) and gets the full (N, D) float32 array in
     input order.  ``encode_local(list_of_id_arrays) -> (n, D)`` is the per-rank encoder; it may return a numpy array
     (CPU / gloo tests) or a torch tensor that already lives on the GPU -- e.g.
     ``lambda d: bulk.encode_sorted_batches_device(d, enc, min_batches_rule=False, to_host=False)`` -- in which case
-    nothing bounces through the host: the all-gather (NCCL over NVLink) and the inverse permutation run on the device."""
+    nothing bounces through the host: the all-gather (NCCL over NVLink) and the inverse permutation run on the device.
+    ``to_host``: True -> numpy on every rank; "rank0" -> numpy on rank 0, the device tensor elsewhere; False -> tensor."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -204,4 +205,6 @@ def encode_bulk_distributed(docs: List[np.ndarray], encode_local: Callable[[List
     sorted_rows = gather_rows(lt.contiguous(), n, world, rank, group)
     inv = torch.as_tensor(order.argsort(), device=sorted_rows.device)
     res = sorted_rows.index_select(0, inv)
+    if to_host == "rank0":        # the reference's driver is one process: only rank 0 needs the array on the host
+        return res.cpu().numpy() if rank == 0 else res
     return res.cpu().numpy() if to_host else res

@@ -104,9 +104,6 @@ struct ie_encoder {
   int use_persistent = 1;  // cooperative persistent kernel; 0 (IE_SEQ=0 or not co-resident): per-timestep fallback
   int persist_checked = 0;
   int cooperative = 1;     // launch attribute (IE_COOP=0: plain launch, co-residency by the occupancy check only)
-  int h_evict_first = 0;   // IE_H_EVICT_FIRST=1 (experiment)
-  int l2_persist = 0;      // IE_L2_PERSIST=1: W_hh of the running layer in the persisting part of the L2 (access-policy window)
-  size_t l2_persist_max = 0;
   int use_mc = 0;          // IE_MC=1: sibling CTA pairs share h tiles by TMA multicast (clusters of four)
   int mc_pairs = 0;        // pairs co-resident in clusters of four
   int batches = 5;         // batches of 256 rows one launch takes (IE_BATCHES, <= kMaxBatches)
@@ -474,11 +471,6 @@ int run_encoder(ie_encoder* h, const int64_t* ids, const int32_t* lengths, int B
         q.gate_mode = h->gate_mode; q.gx_bf16 = h->gx_bf16; q.segs = h->segs;
         q.num_sms = h->num_sms; q.check_only = 0; q.cooperative = h->cooperative; q.fault = h->fault;
         q.diag = h->diag.as<long long>() + 8 * l;
-        q.h_evict_first = h->h_evict_first;
-        if (h->l2_persist) {
-          q.w_ptr = L.w_hh.p;
-          q.w_persist_bytes = std::min<size_t>(h->l2_persist_max, static_cast<size_t>(4) * L.out_pad * ring_mul * L.kh_pad * 2);
-        }
         q.trace = nullptr;
         if (l == h->trace_layer && t0 == 0) {
           const int pairs = ie::lstm_layer_pairs(q);
@@ -617,15 +609,6 @@ int ie_encoder_create(const ie_config* cfg, ie_encoder** out) {
   if (const char* v = getenv("IE_SEQ")) h->use_persistent = atoi(v);
   if (const char* v = getenv("IE_COOP")) h->cooperative = atoi(v);
   if (const char* v = getenv("IE_MC")) h->use_mc = atoi(v);
-  if (const char* v = getenv("IE_L2_PERSIST")) h->l2_persist = atoi(v);
-  if (const char* v = getenv("IE_H_EVICT_FIRST")) h->h_evict_first = atoi(v);
-  if (h->l2_persist) {
-    int max_persist = 0;
-    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, cfg->device);
-    size_t want = std::min<size_t>(static_cast<size_t>(max_persist), 64ull << 20);
-    if (want == 0 || cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) != cudaSuccess) { h->l2_persist = 0; cudaGetLastError(); }
-    h->l2_persist_max = want;
-  }
   if (const char* v = getenv("IE_EMB_PROJ")) h->use_proj = atoi(v);
   if (const char* v = getenv("IE_GX_BF16")) { if (h->segs == 1) h->gx_bf16 = atoi(v); }
   if (const char* v = getenv("IE_FAST_MATH")) { if (h->segs == 1) h->gate_mode = atoi(v) ? 2 : 1; }

@@ -66,9 +66,6 @@ struct LstmLayerArgs {
   CUtensorMap tm_h64;      // same tensor as tm_h with box {64, 64}: the quarter tile one CTA multicasts (mc != 0)
   int mc;                  // 1: clusters of two CTA pairs share every h tile by TMA multicast (needs an even number of tiles)
   int mc_pairs;            // CTA pairs that can be co-resident in clusters of four (lstm_layer_max_pairs() of a check_only query)
-  const void* w_ptr;       // W_hh of the layer and how many bytes of it to keep in the persisting L2 (0: no access-policy window)
-  size_t w_persist_bytes;
-  int h_evict_first;       // experiment: L2 evict-first policy on the h-tile loads
   const void* gx;
   const int* tok;
   float* c;

@@ -80,7 +80,6 @@ struct KArgs {
   long long* trace;
   long long* diag;
   int T, t0, T_total, ng, tiles, out_pad, nkb, segs, kh_pad, gate_mode, trace_items, fault;
-  unsigned long long h_hint;   // L2 cache policy of the h-tile loads
 };
 
 // TOK: Gx rows are rows of the per-token input-projection table; GXBF: Gx / table stored as fp16 (f32 otherwise);
@@ -195,10 +194,10 @@ lstm_layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constan
             // quarter tile: rows [64 * cpair, +64) of this CTA's 128 rows, to this CTA and its counterpart in the sibling pair
             tma_load_2d_pair_mc(ring + stage * stage_bytes + cpair * (a_bytes / 2), &tm_h64, &full[stage],
                                 (seg == 1 ? a.kh_pad : 0) + r * 64, row0 + static_cast<int>(cpair) * 64,
-                                static_cast<uint16_t>(0x5u << crank), a.h_hint);
+                                static_cast<uint16_t>(0x5u << crank), kEvictNormal);
           } else {
             tma_load_2d_pair(ring + stage * stage_bytes, &tm_h, &full[stage], (seg == 1 ? a.kh_pad : 0) + r * 64, row0,
-                             a.h_hint);
+                             kEvictNormal);
           }
           if (++stage == kLStages) { stage = 0; phase ^= 1; }
         }
@@ -444,7 +443,7 @@ cudaError_t launch_layer_t(const LstmLayerArgs& a, int pairs, int tiles, cudaStr
   cfg.blockDim = dim3(kLThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[3];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = MC ? 4 : 2;
   attr[0].val.clusterDim.y = 1;
@@ -473,19 +472,7 @@ cudaError_t launch_layer_t(const LstmLayerArgs& a, int pairs, int tiles, cudaStr
   k.T = a.T; k.t0 = a.t0; k.T_total = a.T_total; k.ng = a.ng; k.tiles = tiles; k.out_pad = a.out_pad;
   k.nkb = a.kh_pad / 64; k.segs = a.segs; k.kh_pad = a.kh_pad; k.gate_mode = a.gate_mode;
   k.trace_items = a.trace_items; k.fault = a.fault;
-  k.h_hint = a.h_evict_first ? kEvictFirst : kEvictNormal;
   cfg.numAttrs = a.cooperative ? 2 : 1;
-  if (a.w_persist_bytes > 0) {
-    // keep this layer's W_hh in the persisting part of the L2 (api.cu sized it with cudaLimitPersistingL2CacheSize):
-    // every timestep re-reads all of it, and an L2 miss in the operand stream stalls the MMA thread for a DRAM latency
-    cudaLaunchAttribute& w = attr[cfg.numAttrs++];
-    w.id = cudaLaunchAttributeAccessPolicyWindow;
-    w.val.accessPolicyWindow.base_ptr = const_cast<void*>(a.w_ptr);
-    w.val.accessPolicyWindow.num_bytes = a.w_persist_bytes;
-    w.val.accessPolicyWindow.hitRatio = 1.0f;
-    w.val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-    w.val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-  }
   return cudaLaunchKernelEx(&cfg, kfn, a.tm_h, a.tm_w, a.tm_h64, k);
 }
 

@@ -243,6 +243,34 @@ def test_every_path_gives_identical_bits(knobs, monkeypatch):
     exp.close()
 
 
+def test_shape_sweep_vs_oracle_and_bulk_pipeline(monkeypatch):
+    """Batch sizes around every internal boundary (1, 256 +- 1, 512 +- 1, 1280 +- 1: batches per launch, slices of the host
+    shim) x sequence lengths down to a single token, ragged lengths, against the oracle; then the bulk pipeline
+    (length sort, pinned double-buffered staging, device un-sort) on 3000 ragged issues against row-by-row calls."""
+    cfg = (2, 64, 128, 300)
+    ref = R.make_encoder(11, cfg[3], cfg[1], cfg[2], cfg[0], scale=2.0)
+    enc = _make(cfg, ref.export_weights(), monkeypatch)
+    rng = np.random.default_rng(0)
+    for B in (1, 2, 255, 256, 257, 511, 513, 1279, 1280, 1281, 1300):
+        for T in (1, 2, 3, 17):
+            docs = R.synthetic_ids(B, T, seed=B * 31 + T, vocab_sz=cfg[3], min_len=1)
+            ids, lengths = _pad(docs, T)
+            got = enc.encode_ids(ids, lengths)
+            sel = rng.choice(B, size=min(B, 24), replace=False)
+            want = R.encode_padded(ref, ids[sel], lengths[sel])
+            m = R.parity_metrics(got[sel], want)
+            assert np.isfinite(got).all() and m["min_cosine"] >= COS_MIN and m["rel_l2"] <= REL_L2_MAX_SCALED, (B, T, m)
+            np.testing.assert_array_equal(got[-1], enc.encode_ids(ids[-1:, :lengths[-1]])[0])   # last row, alone, unpadded
+    docs = R.synthetic_ids(3000, 40, seed=5, vocab_sz=cfg[3], min_len=1)
+    bulk_out = enc.encode_id_list(docs, bs=100)
+    assert bulk_out.shape == (3000, 192)
+    for i in rng.choice(3000, size=40, replace=False):
+        np.testing.assert_array_equal(bulk_out[i], enc.encode_ids(docs[i][None, :])[0])
+    with pytest.raises(ValueError):
+        enc.encode_id_list([np.array([2, 5, 299, 300])])                        # token id outside the vocabulary
+    enc.close()
+
+
 # ------------------------------------------------------------------------------------------------ full-size goldens
 def _golden_full(golden_dir, name):
     z = np.load(os.path.join(golden_dir, name))
