@@ -25,7 +25,7 @@ def encode_sorted_batches(docs: List[np.ndarray], encode_padded: Callable, pad_i
     ``coalesce=True``: consecutive sorted batches are merged into device calls of ``max_bs`` rows.  On the B200 path a
     row's result does not depend on its batch mates or on the padded length (bit-exact, tests/test_gpu_parity.py), so
     ``bs`` -- a memory knob of the reference, default 100 -- only decides how many rows ride one launch; merging keeps
-    the results and lets a caller with the reference's default arguments reach the 768-row kernels."""
+    the results and lets a caller with the reference's default arguments reach full 1280-row launches."""
     n = len(docs)
     if n == 0:
         return np.empty((0, out_dim), dtype=np.float32)
