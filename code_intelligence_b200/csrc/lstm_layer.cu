@@ -16,13 +16,14 @@
 //     increasing order, so the item with the globally smallest index can always run: no wait cycle for any P, C, T.
 //     With C >= 2P + tiles (five batches at H = 2400: 190 >= 148 + 38) an item's inputs were finished two rounds
 //     earlier and every pair issues MMAs back to back;
-//   * per item: K/64 k-blocks of h (TMA, 128B swizzle, 3-stage ring) and W_hh (own ring, free-running: weights do not
-//     depend on the step) -> 4 x tcgen05.mma per k-block into one of two TMEM accumulator slots -> 16 epilogue warps
+//   * per item: K/64 k-blocks of h and W_hh (TMA, 128B swizzle) through ONE 7-stage ring -- two producer threads fill
+//     the halves of a stage independently (weights do not depend on the step, so their producer runs ahead of the h
+//     dependency) -> 4 x tcgen05.mma per k-block into one of two TMEM accumulator slots -> 16 epilogue warps
 //     (tcgen05.ld, + Gx, gates, c_t, h_t as bf16 into slot t+1 of the hidden-state ring = next step's A operand and the
-//     next layer's GEMM input) -> gpu-scope fence + red.add on the (step, batch) counter;
+//     next layer's GEMM input; full 32-byte sectors per store) -> gpu-scope fence + red.add on the (step, batch) counter;
 //   * the cell state moves between SMs from step to step: it lives in global memory (L2) and is read with ld.global.cg
-//     after the pair has seen the (t-1, g) counter; the pooling accumulators of the last layer are L2 reductions
-//     (lstm_common.cuh), so neither sits on the step's critical path;
+//     after the pair has seen the (t-1, g) counter; on the last layer the running max of the concat-pool travels the same
+//     way and the pooled sum is an L2 reduction (lstm_common.cuh), so none of them sits on the step's critical path;
 //   * split-bf16 ("fp32-accurate") mode: segs = 3 runs the K loop over [h_hi | h_lo | h_hi] x [W_hi | W_hi | W_lo]
 //     (hi = bf16(x), lo = bf16(x - hi); the dropped lo*lo term is 2^-18 relative) -- same kernel, three times the MMAs.
 //

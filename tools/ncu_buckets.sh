@@ -3,8 +3,10 @@
 set -u
 mkdir -p gpurun_out; O=gpurun_out; TAG=${1:-nb}
 for T in 64 128 256 512 1024 2048; do
-  timeout 600 ncu --metrics gpu__time_duration.sum,sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed,dram__bytes_read.sum,dram__bytes_write.sum \
-    --clock-control none --csv --log-file $O/ncu_bucket_${T}_$TAG.csv python tools/profile_step.py --B 1280 --T $T --warm 1 --iters 1 > /dev/null 2>&1
+  # application replay: the cooperative cluster launch of the persistent kernel does not survive ncu's kernel replay
+  # when more than one pass is needed
+  timeout 900 ncu --replay-mode application --metrics gpu__time_duration.sum,sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed,dram__bytes_read.sum,dram__bytes_write.sum \
+    -k regex:"lstm_layer|gemm_bf16_pair" --clock-control none --csv --log-file $O/ncu_bucket_${T}_$TAG.csv python tools/profile_step.py --B 1280 --T $T --warm 1 --iters 1 > $O/ncu_bucket_${T}_$TAG.out 2>&1
 done
 python - <<PY
 import csv, json
@@ -15,9 +17,16 @@ for T in (64, 128, 256, 512, 1024, 2048):
     except Exception as e:
         continue
     h = rows[0]; ki = h.index('Kernel Name'); mi = h.index('Metric Name'); vi = h.index('Metric Value'); ii = h.index('ID')
+    ui = h.index('Metric Unit')
+    def fl(x):
+        try: return float(x.replace(',', ''))
+        except Exception: return 0.0
     per = {}
     for r in rows[1:]:
-        per.setdefault(r[ii], {'k': r[ki]})[r[mi]] = float(r[vi].replace(',', ''))
+        v = fl(r[vi])
+        if r[mi] == 'gpu__time_duration.sum': v *= {'ns': 1.0, 'us': 1e3, 'ms': 1e6, 's': 1e9}.get(r[ui], 1.0)          # -> ns
+        if r[mi].startswith('dram__bytes'): v *= {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}.get(r[ui], 1.0)  # -> bytes
+        per.setdefault(r[ii], {'k': r[ki]})[r[mi]] = v
     # the second encode only (skip the warm-up call): launches are in order; take the last half of the ie:: launches
     ls = [v for k, v in sorted(per.items(), key=lambda x: int(x[0])) if 'ie::' in v['k'] and 'convert_rows' not in v['k']]
     ls = ls[len(ls) // 2:]
