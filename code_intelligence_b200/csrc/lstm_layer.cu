@@ -91,11 +91,11 @@ struct KArgs {
 //     items.  The kernel is bound by L2 -> SM bytes (both operands stream from L2 at ~9.5 TB/s chip-wide, the practical
 //     LTS limit -- profiles/README.md); this removes a quarter of them.  A stage is refilled only when BOTH pairs have
 //     consumed it (empty barriers count two commits, each multicast to all four CTAs).
-// Cluster dimensions come from the launch (cudaLaunchAttributeClusterDimension: 2, or 4 with MC).
+// The body is shared by two __global__ wrappers below: the production kernel with compile-time clusters of two, and
+// the multicast variant whose clusters of four come from the launch attribute.
 template <bool TOK, bool GXBF, bool POOL, bool MC>
-__global__ void __launch_bounds__(kLThreads, 1)
-lstm_layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ CUtensorMap tm_w,
-                  const __grid_constant__ CUtensorMap tm_h64, const __grid_constant__ KArgs a) {
+__device__ __forceinline__ void lstm_layer_body(const CUtensorMap& tm_h, const CUtensorMap& tm_w,
+                                                const CUtensorMap& tm_h64, const KArgs& a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t rawaddr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (rawaddr & 1023u)) & 1023u);
@@ -424,13 +424,29 @@ lstm_layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constan
 
 thread_local int g_last_max_pairs = 0;   // result of the last check_only query on this thread
 
+template <bool TOK, bool GXBF, bool POOL>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kLThreads, 1)
+lstm_layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ CUtensorMap tm_w,
+                  const __grid_constant__ CUtensorMap tm_h64, const __grid_constant__ KArgs a) {
+  lstm_layer_body<TOK, GXBF, POOL, false>(tm_h, tm_w, tm_h64, a);
+}
+
+template <bool TOK>
+__global__ void __launch_bounds__(kLThreads, 1)
+lstm_layer_mc_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ CUtensorMap tm_w,
+                     const __grid_constant__ CUtensorMap tm_h64, const __grid_constant__ KArgs a) {
+  lstm_layer_body<TOK, true, false, true>(tm_h, tm_w, tm_h64, a);
+}
+
 size_t layer_smem_bytes() {
   return 1024 + static_cast<size_t>(kLStages) * (128 * 64 * 2 + kLHalfRows * 64 * 2) + (2 * kLStages + 4) * 8 + 32;
 }
 
 template <bool TOK, bool GXBF, bool POOL, bool MC>
 cudaError_t launch_layer_t(const LstmLayerArgs& a, int pairs, int tiles, cudaStream_t stream) {
-  auto kfn = lstm_layer_kernel<TOK, GXBF, POOL, MC>;
+  void (*kfn)(CUtensorMap, CUtensorMap, CUtensorMap, KArgs);
+  if constexpr (MC) kfn = lstm_layer_mc_kernel<TOK>;
+  else kfn = lstm_layer_kernel<TOK, GXBF, POOL>;
   const size_t smem = layer_smem_bytes();
   // function attributes are per device: set on every launch (cheap), never cached in a process-wide flag
   cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
@@ -445,14 +461,16 @@ cudaError_t launch_layer_t(const LstmLayerArgs& a, int pairs, int tiles, cudaStr
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = MC ? 4 : 2;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  attr[1].id = cudaLaunchAttributeCooperative;
-  attr[1].val.cooperative = 1;
+  int na = 0;
+  if (MC) {   // the production kernel carries __cluster_dims__(2, 1, 1)
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 4;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = na;
   if (a.check_only) {
     // how many CTA pairs can be co-resident with this cluster shape (returned through a.check_only's contract: the
     // caller reads lstm_layer_max_pairs())
@@ -473,7 +491,12 @@ cudaError_t launch_layer_t(const LstmLayerArgs& a, int pairs, int tiles, cudaStr
   k.T = a.T; k.t0 = a.t0; k.T_total = a.T_total; k.ng = a.ng; k.tiles = tiles; k.out_pad = a.out_pad;
   k.nkb = a.kh_pad / 64; k.segs = a.segs; k.kh_pad = a.kh_pad; k.gate_mode = a.gate_mode;
   k.trace_items = a.trace_items; k.fault = a.fault;
-  cfg.numAttrs = a.cooperative ? 2 : 1;
+  if (a.cooperative) {
+    attr[na].id = cudaLaunchAttributeCooperative;
+    attr[na].val.cooperative = 1;
+    ++na;
+  }
+  cfg.numAttrs = na;
   return cudaLaunchKernelEx(&cfg, kfn, a.tm_h, a.tm_w, a.tm_h64, k);
 }
 

@@ -141,6 +141,27 @@ __global__ void convert_rows_kernel(const float* __restrict__ src, long long ld_
   }
 }
 
+// Row-contiguous fast path of convert_rows_kernel (the MLP head's X f32 -> bf16 pass, the largest stream of that path):
+// no permutation, cols % 4 == 0; one warp per row, 128-bit loads, 64-bit stores, zero fill of the K padding.
+__global__ void convert_rows_vec_kernel(const float* __restrict__ src, long long ld_src, int cols, int rows,
+                                        __nv_bfloat16* __restrict__ dst, long long ld_dst) {
+  const int warps_per_block = blockDim.x >> 5;
+  const long long r = static_cast<long long>(blockIdx.x) * warps_per_block + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const float4* s4 = reinterpret_cast<const float4*>(src + r * ld_src);
+  uint2* d2 = reinterpret_cast<uint2*>(dst + r * ld_dst);
+  const int n4 = cols >> 2, w4 = static_cast<int>(ld_dst >> 2);
+  for (int i = lane; i < w4; i += 32) {
+    uint2 o = make_uint2(0u, 0u);
+    if (i < n4) {
+      const float4 v = __ldcs(s4 + i);   // streaming: read once
+      o = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+    }
+    d2[i] = o;
+  }
+}
+
 __global__ void fill_f32_kernel(float* p, size_t n, float v) {
   size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
@@ -185,6 +206,12 @@ cudaError_t launch_prep_lengths(const int* lengths_in, int B, int T, int b_pad, 
 cudaError_t launch_convert_rows(const float* src, long long ld_src, int cols, const int* perm, int rows_dst,
                                 __nv_bfloat16* dst, long long ld_dst, int lo_off, cudaStream_t stream) {
   if (lo_off > 0 && ld_dst < 2ll * lo_off) return cudaErrorInvalidValue;
+  if (perm == nullptr && lo_off == 0 && cols % 4 == 0 && ld_src % 4 == 0 && ld_dst % 4 == 0 &&
+      (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 7) == 0) {
+    const int wpb = 8;
+    convert_rows_vec_kernel<<<(rows_dst + wpb - 1) / wpb, wpb * 32, 0, stream>>>(src, ld_src, cols, rows_dst, dst, ld_dst);
+    return cudaGetLastError();
+  }
   convert_rows_kernel<<<rows_dst, 256, 0, stream>>>(src, ld_src, cols, perm, rows_dst, dst, ld_dst, lo_off);
   return cudaGetLastError();
 }
