@@ -15,7 +15,7 @@ LIB_PATH = _PKG / "libissue_emb_b200.so"
 
 IE_OK, IE_ERR_INVALID, IE_ERR_CUDA, IE_ERR_OOM, IE_ERR_STATE, IE_ERR_TOKEN = 0, -1, -2, -3, -4, -5
 IE_FLAG_DEVICE_PTRS = 1
-IE_MAX_BATCH = 2048          # upper bound; a handle's own limit is ie_encoder_max_batch() (1280 by default)
+IE_MAX_BATCH = 3072          # upper bound; a handle's own limit is ie_encoder_max_batch() (1280 by default)
 IE_CFG_ACCURATE_GATES, IE_CFG_FP32, IE_CFG_F32_GX = 1, 2, 4
 
 

@@ -358,7 +358,8 @@ int run_encoder(ie_encoder* h, const int64_t* ids, const int32_t* lengths, int B
     return fail(IE_ERR_OOM, "B_pad*T = %lld tokens exceeds the workspace cap %lld; use a smaller batch",
                 static_cast<long long>(b_pad) * T, cap);
   CK(cudaSetDevice(c.device));
-  long long chunk_T = std::max<long long>(1, (1ll << 20) / b_pad);  // <= 2^20 (timestep, row) pairs of Gx at once
+  // <= 2^21 (timestep, row) pairs of Gx at once (40 GB as fp16 at H = 2400); half of that with f32 projections
+  long long chunk_T = std::max<long long>(1, ((h->gx_bf16 ? 2ll : 1ll) << 20) / b_pad);
   if (h->chunk_t > 0) chunk_T = h->chunk_t;
   chunk_T = std::min<long long>(chunk_T, T);
   const bool proj = proj_usable(h);
@@ -541,7 +542,7 @@ int run_encoder(ie_encoder* h, const int64_t* ids, const int32_t* lengths, int B
   h->has_done = true;
   h->last_stream = s;
   // a handle that once served a very long sequence does not keep tens of GB for ever
-  if (h->ws_tokens > (1ll << 20) && std::min<long long>(rows, chunk_T * b_pad) * 8 < h->ws_tokens) {
+  if (h->ws_tokens > (1ll << 21) && std::min<long long>(rows, chunk_T * b_pad) * 8 < h->ws_tokens) {
     if (++h->small_calls >= 4) {
       CK(cudaStreamSynchronize(s));
       release_workspace(h);

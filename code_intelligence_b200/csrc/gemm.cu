@@ -480,11 +480,8 @@ cudaError_t launch_gemm_bf16(const GemmArgs& g, cudaStream_t stream) {
   e = make_tmap_bf16_2d(&tmB, g.b, k_inner, g.n_pad, g.ldb, kBlockK, g.bn);
   if (e != cudaSuccess) return e;
 
-  static int use_pair = -1;
-  if (use_pair < 0) {
-    const char* e = getenv("IE_GEMM_PAIR");
-    use_pair = e ? atoi(e) : 1;
-  }
+  const char* pair_env = getenv("IE_GEMM_PAIR");   // IE_GEMM_PAIR=0: single-CTA kernel (development knob)
+  const int use_pair = pair_env ? atoi(pair_env) : 1;
   const int sms0 = g.num_sms > 0 ? g.num_sms : 148;
   if (use_pair && g.m_pad % 256 == 0 && g.bn % 16 == 0 && (g.m_pad / 256) * (g.n_pad / g.bn) >= sms0 / 2) {
     // CTA-pair path: M = 256 tiles

@@ -60,7 +60,7 @@ cudaError_t launch_lstm_step(const LstmStepArgs& a, cudaStream_t stream);
 
 // ---- persistent recurrent layer (lstm_layer.cu): all timesteps of a layer (or of a time chunk) in one cooperative launch,
 //      up to kMaxBatches batches of 256 rows; (timestep, batch, tile) items dealt round-robin over all CTA pairs
-constexpr int kMaxBatches = 8;
+constexpr int kMaxBatches = 12;
 struct LstmLayerArgs {
   CUtensorMap tm_h, tm_w;  // as LstmStepArgs
   CUtensorMap tm_h64;      // same tensor as tm_h with box {64, 64}: the quarter tile one CTA multicasts (mc != 0)

@@ -51,7 +51,7 @@ extern "C" {
                                 /* relative per product), input projections kept in f32, IEEE gates.  ~3x the MMAs.    */
 #define IE_CFG_F32_GX 4         /* keep the hoisted input projections in f32 instead of fp16 (bf16 mode only)         */
 
-#define IE_MAX_BATCH 2048 /* upper bound of rows per ie_encoder_encode call; the handle's own limit is
+#define IE_MAX_BATCH 3072 /* upper bound of rows per ie_encoder_encode call; the handle's own limit is
                              ie_encoder_max_batch() = 256 x (batches per launch, default 5): that many independent
                              256-row batches ride one launch of the persistent recurrent kernel (each a CTA-pair
                              M=256 UMMA tile); they share the kernel, not their results */
@@ -111,7 +111,7 @@ int ie_encoder_raw_features(ie_encoder* h, const int64_t* ids, int32_t B, int32_
 int64_t ie_encoder_launch_count(const ie_encoder* h);
 
 /* Rows one ie_encoder_encode call accepts on this handle: 1280 = five 256-row batches per launch by default
- * (environment variable IE_BATCHES=n at create time, 1 <= n <= 8, changes that to 256 n). */
+ * (environment variable IE_BATCHES=n at create time, 1 <= n <= 12, changes that to 256 n). */
 int32_t ie_encoder_max_batch(const ie_encoder* h);
 
 /* Device-side error state of the last call on this handle (waits for it to finish): IE_OK, IE_ERR_TOKEN (a token id

@@ -221,7 +221,9 @@ def _make(cfg, weights, monkeypatch, env=None, flags=0):
 @pytest.mark.parametrize("knobs", [{"IE_SEQ": 0}, {"IE_EMB_PROJ": 0}, {"IE_EMB_PROJ": 0, "IE_SEQ": 0}, {"IE_BATCHES": 3},
                                    {"IE_BATCHES": 8}, {"IE_CHUNK_T": 5}, {"IE_CHUNK_T": 1, "IE_EMB_PROJ": 0}, {"IE_COOP": 0},
                                    {"IE_MC": 1}, {"IE_MC": 0}, {"IE_MC": 1, "IE_BATCHES": 4, "IE_CHUNK_T": 7},
-                                   {"IE_GX_BF16": 0, "_base": {"IE_GX_BF16": 0, "IE_SEQ": 0, "IE_CHUNK_T": 3}}])
+                                   {"IE_GX_BF16": 0, "_base": {"IE_GX_BF16": 0, "IE_SEQ": 0, "IE_CHUNK_T": 3}},
+                                   {"IE_FAST_MATH": 0, "_base": {"IE_FAST_MATH": 0, "IE_SEQ": 0}},
+                                   {"IE_BATCHES": 12, "IE_MC": 1}])
 def test_every_path_gives_identical_bits(knobs, monkeypatch):
     """One persistent kernel (csrc/lstm_layer.cu) + one fallback (csrc/lstm.cu, IE_SEQ=0) share the cell arithmetic of
     csrc/lstm_common.cuh; the per-token input-projection table is the same GEMM on the same operands as gather + GEMM;

@@ -26,3 +26,6 @@ PY
 echo "== ncu per bucket (application replay)"
 bash tools/ncu_buckets.sh $TAG
 tail -2 $O/ncu_bucket_512_$TAG.out | cut -c1-300
+echo "== batches per launch A/B"
+timeout 600 python tools/power_probe.py --seconds 3 --what "enc,enc:IE_BATCHES=8,enc:IE_BATCHES=10,enc:IE_BATCHES=12,enc" > $O/power_$TAG.jsonl 2> $O/power_$TAG.err
+echo "rc=$?"; cut -c1-720 $O/power_$TAG.jsonl; tail -3 $O/power_$TAG.err
