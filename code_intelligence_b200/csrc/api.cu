@@ -85,6 +85,7 @@ struct Layer {
   int kh_pad = 0;           // padded K of the recurrent projection
   int bn = 0;               // GEMM N tile for the input projection
   DevBuf w_ih, w_hh, bias;  // sliced layouts
+  DevBuf w_cat;             // last layer: rows [W_ih (kin_pad) | W_hh (kh_pad)] for the fused input projection
   bool loaded = false;
 };
 
@@ -106,7 +107,10 @@ struct ie_encoder {
   int cooperative = 1;     // launch attribute (IE_COOP=0: plain launch, co-residency by the occupancy check only)
   int use_mc = 0;          // IE_MC=1: sibling CTA pairs share h tiles by TMA multicast (clusters of four)
   int mc_pairs = 0;        // pairs co-resident in clusters of four
+  int fuse_prefetch = 1;   // fused last layer: L2 prefetch of the next item's x tiles (IE_FUSE_PREFETCH)
   int batches = 5;         // batches of 256 rows one launch takes (IE_BATCHES, <= kMaxBatches)
+  int fuse_last = 1;       // the last layer's input projection rides its recurrent K loop (lstm_layer.cu FUSE) instead of a
+                           // hoisted GEMM + Gx round trip (IE_FUSE_LAST=0: hoisted like the other layers)
   int max_batch = 1280;
   // layer 0's input projection W_ih0 . Emb[id] + b depends on the token id alone: tabulated once per weight set
   // (proj: [vocab_pad, 4*out_pad], computed by the same GEMM from the same operands => the same bits as gather + GEMM)
@@ -419,26 +423,37 @@ int run_encoder(ie_encoder* h, const int64_t* ids, const int32_t* lengths, int B
     if ((rc = mark(h, 1, s)) != IE_OK) return rc;
     int cur = 0;
     const __nv_bfloat16* layer_in = h->x0.as<__nv_bfloat16>();
+    const __nv_bfloat16* prev_ring = nullptr;  // the previous layer's ring (slot 0 included)
     long long layer_in_ld = ring_mul * h->e_pad;
     for (int l = 0; l < c.n_layers; ++l) {
       const bool last = (l == c.n_layers - 1);
       Layer& L = h->layers[l];
       const bool from_table = proj && l == 0;  // Gx rows of layer 0 are rows of the per-token table: no GEMM
+      // last layer: input projection fused into the recurrent K loop (no GEMM, no Gx)
+      const bool fused = persistent && last && l > 0 && h->segs == 1 && h->fuse_last && L.w_cat.p != nullptr;
       __nv_bfloat16* ybuf = h->y[cur].as<__nv_bfloat16>();
       __nv_bfloat16* carry = h->hcarry.as<__nv_bfloat16>() + static_cast<size_t>(l) * carry_layer;
       float* cstate = h->c.as<float>() + static_cast<size_t>(l) * h->max_batch * mop;
       CUtensorMap tm_h, tm_w;
       CK(ie::make_tmap_bf16_2d(&tm_h, ybuf, static_cast<uint64_t>(ring_mul) * L.kh_pad, static_cast<uint64_t>(crow + b_pad),
                                h->y_ld, 64, 128));
-      CK(ie::make_tmap_bf16_2d(&tm_w, L.w_hh.p, static_cast<uint64_t>(ring_mul) * L.kh_pad, 4ull * L.out_pad,
-                               static_cast<uint64_t>(ring_mul) * L.kh_pad, 64, 128));
+      if (fused)
+        CK(ie::make_tmap_bf16_2d(&tm_w, L.w_cat.p, static_cast<uint64_t>(L.kin_pad + L.kh_pad), 4ull * L.out_pad,
+                                 static_cast<uint64_t>(L.kin_pad + L.kh_pad), 64, 128));
+      else
+        CK(ie::make_tmap_bf16_2d(&tm_w, L.w_hh.p, static_cast<uint64_t>(ring_mul) * L.kh_pad, 4ull * L.out_pad,
+                                 static_cast<uint64_t>(ring_mul) * L.kh_pad, 64, 128));
       CUtensorMap tm_h64 = tm_h;
+      CUtensorMap tm_x = tm_h;
+      if (fused)
+        CK(ie::make_tmap_bf16_2d(&tm_x, prev_ring, static_cast<uint64_t>(L.kin_pad), static_cast<uint64_t>(crow + b_pad),
+                                 h->y_ld, 64, 128));
       if (h->use_mc)
         CK(ie::make_tmap_bf16_2d(&tm_h64, ybuf, static_cast<uint64_t>(ring_mul) * L.kh_pad,
                                  static_cast<uint64_t>(crow + b_pad), h->y_ld, 64, 64));
       // slot 0 of the ring = this layer's h at the end of the previous chunk (zeros before the first)
       CK(cudaMemcpyAsync(ybuf, carry, slot_bytes, cudaMemcpyDeviceToDevice, s));
-      if (!from_table) {
+      if (!from_table && !fused) {
         // hoisted input projection over the chunk's Tc*b_pad rows
         ie::GemmArgs g{};
         fill_gemm(h, L, g);
@@ -457,6 +472,7 @@ int run_encoder(ie_encoder* h, const int64_t* ids, const int32_t* lengths, int B
         CK(cudaMemsetAsync(h->step_done.p, 0, static_cast<size_t>(Tc) * ng * sizeof(unsigned), s));
         ie::LstmLayerArgs q{};
         q.tm_h = tm_h; q.tm_w = tm_w; q.tm_h64 = tm_h64; q.mc = h->use_mc; q.mc_pairs = h->mc_pairs;
+        q.tm_x = tm_x; q.pre_nkb = fused ? L.kin_pad / 64 : 0; q.bias = L.bias.as<float>(); q.prefetch_x = h->fuse_prefetch;
         q.gx = from_table ? h->proj.p : h->gx.p;
         q.tok = from_table ? h->tok.as<int>() : nullptr;
         q.c = cstate; q.y = ybuf;
@@ -515,6 +531,7 @@ int run_encoder(ie_encoder* h, const int64_t* ids, const int32_t* lengths, int B
       if (t0 + Tc < T)  // carry h of the chunk's last step into the next chunk
         CK(cudaMemcpyAsync(carry, ybuf + static_cast<size_t>(Tc) * b_pad * h->y_ld, slot_bytes, cudaMemcpyDeviceToDevice, s));
       if ((rc = mark(h, 3 + 2 * l, s)) != IE_OK) return rc;
+      prev_ring = ybuf;
       layer_in = ybuf + static_cast<long long>(b_pad) * h->y_ld;  // slot 1 onwards
       layer_in_ld = h->y_ld;
       cur ^= 1;
@@ -613,6 +630,8 @@ int ie_encoder_create(const ie_config* cfg, ie_encoder** out) {
   if (const char* v = getenv("IE_EMB_PROJ")) h->use_proj = atoi(v);
   if (const char* v = getenv("IE_GX_BF16")) { if (h->segs == 1) h->gx_bf16 = atoi(v); }
   if (const char* v = getenv("IE_FAST_MATH")) { if (h->segs == 1) h->gate_mode = atoi(v) ? 2 : 1; }
+  if (const char* v = getenv("IE_FUSE_LAST")) h->fuse_last = atoi(v);
+  if (const char* v = getenv("IE_FUSE_PREFETCH")) h->fuse_prefetch = atoi(v);
   if (const char* v = getenv("IE_BATCHES")) h->batches = std::min(ie::kMaxBatches, std::max(1, atoi(v)));
   if (const char* v = getenv("IE_SPIN_LIMIT_MS")) h->spin_limit = static_cast<long long>(atof(v) * 1.9e6);
   if (const char* v = getenv("IE_DEBUG_FAULT")) h->fault = atoi(v);
@@ -630,7 +649,7 @@ void ie_encoder_destroy(ie_encoder* h) {
   if (h == nullptr) return;
   cudaSetDevice(h->cfg.device);
   cudaDeviceSynchronize();
-  for (Layer& L : h->layers) { L.w_ih.release(); L.w_hh.release(); L.bias.release(); }
+  for (Layer& L : h->layers) { L.w_ih.release(); L.w_hh.release(); L.bias.release(); L.w_cat.release(); }
   DevBuf* bufs[] = {&h->emb, &h->ids, &h->len_in, &h->lengths, &h->x0, &h->y[0], &h->y[1], &h->gx, &h->c, &h->pool_sum,
                     &h->pool_max, &h->pool_last, &h->out, &h->raw, &h->err, &h->step_done, &h->trace, &h->proj, &h->tok,
                     &h->diag, &h->hcarry};
@@ -673,6 +692,15 @@ int ie_encoder_load_layer(ie_encoder* h, int32_t layer, const float* w_ih, const
   for (size_t r = 0; r < perm.size(); ++r) bias[r] = perm[r] < 0 ? 0.0f : b_ih[perm[r]] + b_hh[perm[r]];
   CK(L.bias.reserve(bias.size() * sizeof(float)));
   CK(cudaMemcpy(L.bias.p, bias.data(), bias.size() * sizeof(float), cudaMemcpyHostToDevice));
+  if (layer == h->cfg.n_layers - 1 && layer > 0 && h->segs == 1) {
+    // [W_ih | W_hh] row by row: the B operand of the fused last layer (one tensor map, K = kin_pad + kh_pad)
+    const size_t kc = static_cast<size_t>(L.kin_pad) + L.kh_pad, rows = 4 * static_cast<size_t>(L.out_pad);
+    CK(L.w_cat.reserve(rows * kc * sizeof(__nv_bfloat16)));
+    CK(cudaMemcpy2D(L.w_cat.p, kc * 2, L.w_ih.p, static_cast<size_t>(L.kin_pad) * 2, static_cast<size_t>(L.kin_pad) * 2, rows,
+                    cudaMemcpyDeviceToDevice));
+    CK(cudaMemcpy2D(L.w_cat.as<__nv_bfloat16>() + L.kin_pad, kc * 2, L.w_hh.p, static_cast<size_t>(L.kh_pad) * 2,
+                    static_cast<size_t>(L.kh_pad) * 2, rows, cudaMemcpyDeviceToDevice));
+  }
   L.loaded = true;
   if (layer == 0) h->proj_built = false;
   return IE_OK;

@@ -64,6 +64,12 @@ constexpr int kMaxBatches = 12;
 struct LstmLayerArgs {
   CUtensorMap tm_h, tm_w;  // as LstmStepArgs
   CUtensorMap tm_h64;      // same tensor as tm_h with box {64, 64}: the quarter tile one CTA multicasts (mc != 0)
+  CUtensorMap tm_x;        // pre_nkb > 0: the PREVIOUS layer's ring (slot t+1 = this layer's x_t), box {64, 128}
+  int pre_nkb;             // > 0: fuse the input projection into the K loop -- pre_nkb = kin_pad / 64 k-blocks of
+                           // x_t W_ih^T precede the recurrent ones; tm_w then covers [W_ih | W_hh] (inner kin_pad + kh_pad),
+                           // gx is unused and `bias` (b_ih + b_hh, permuted like the weight rows) is added instead
+  const float* bias;
+  int prefetch_x;          // fused form: L2 prefetch of the next item's x tiles (default on; IE_FUSE_PREFETCH=0)
   int mc;                  // 1: clusters of two CTA pairs share every h tile by TMA multicast (needs an even number of tiles)
   int mc_pairs;            // CTA pairs that can be co-resident in clusters of four (lstm_layer_max_pairs() of a check_only query)
   const void* gx;

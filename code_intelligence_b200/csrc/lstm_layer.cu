@@ -67,6 +67,7 @@ __device__ __forceinline__ void wait_seq_ge(const uint32_t* p, uint32_t target, 
 struct KArgs {
   const void* gx;        // f32 or bf16 [rows, 4*out_pad]; row = t_local*b_pad + brow, or the token id (TOK)
   const int* tok;        // TOK: time-major token ids of the whole call, index (t0 + t)*b_pad + brow
+  const float* bias;     // FUSE: b_ih + b_hh in the permuted column order (takes the place of Gx)
   float* cstate;         // [b_pad, out_pad]
   __nv_bfloat16* y;      // ring [(T+1)*b_pad, ldy] of this time chunk: slot 0 = h before the chunk, slot t+1 = h_t
   float* raw;            // optional [b_pad, T_total, raw_ld]
@@ -81,6 +82,8 @@ struct KArgs {
   long long* trace;
   long long* diag;
   int T, t0, T_total, ng, tiles, out_pad, nkb, segs, kh_pad, gate_mode, trace_items, fault;
+  int pre_nkb;           // FUSE: k-blocks of the input projection that precede the recurrent ones in every item
+  int prefetch_x;        // FUSE: L2 prefetch of the next item's x tiles by the watcher thread
 };
 
 // TOK: Gx rows are rows of the per-token input-projection table; GXBF: Gx / table stored as fp16 (f32 otherwise);
@@ -91,11 +94,21 @@ struct KArgs {
 //     items.  The kernel is bound by L2 -> SM bytes (both operands stream from L2 at ~9.5 TB/s chip-wide, the practical
 //     LTS limit -- profiles/README.md); this removes a quarter of them.  A stage is refilled only when BOTH pairs have
 //     consumed it (empty barriers count two commits, each multicast to all four CTAs).
+// FUSE: the layer's input projection rides the recurrent K loop instead of a hoisted GEMM + Gx round trip: every item
+//     first accumulates x_t W_ih^T -- pre_nkb k-blocks whose A operand is slot t+1 of the PREVIOUS layer's ring (tm_x)
+//     and whose B operand is the W_ih part of the concatenated weights [W_ih | W_hh] (tm_w) -- and then, once the
+//     (t-1, g) counter has been seen, the nkb k-blocks of h_{t-1} W_hh^T into the same accumulator; the epilogue adds
+//     the bias (f32) where the other instantiations add Gx.  Used for the 800-wide last layer, whose 13 tiles x 5
+//     batches cannot fill 74 pairs: its step chain (MMAs 7.5 us + epilogue + publish + counter + first tile ~ 20 us per
+//     timestep) left the tensor pipe idle 80 % of the time, and the independent W_ih k-blocks now run inside that wait
+//     (the dependency of item k resolves while the pair issues the 38 input-projection k-blocks of item k).  The sum
+//     W_ih x + W_hh h + b stays in f32 (no fp16 rounding of Gx), so the fused layer is slightly MORE accurate than the
+//     hoisted form, but its bits differ from the fallback kernel's (tests compare those two with IE_FUSE_LAST=0).
 // The body is shared by two __global__ wrappers below: the production kernel with compile-time clusters of two, and
 // the multicast variant whose clusters of four come from the launch attribute.
-template <bool TOK, bool GXBF, bool POOL, bool MC>
+template <bool TOK, bool GXBF, bool POOL, bool MC, bool FUSE>
 __device__ __forceinline__ void lstm_layer_body(const CUtensorMap& tm_h, const CUtensorMap& tm_w,
-                                                const CUtensorMap& tm_h64, const KArgs& a) {
+                                                const CUtensorMap& tm_h64, const CUtensorMap& tm_x, const KArgs& a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t rawaddr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (rawaddr & 1023u)) & 1023u);
@@ -140,12 +153,14 @@ __device__ __forceinline__ void lstm_layer_body(const CUtensorMap& tm_h, const C
   const long long total = static_cast<long long>(a.T) * C;
   const int b_pad = 256 * ng;
   const unsigned batch_ctas = 2u * static_cast<unsigned>(tiles);  // CTAs that publish a (step, batch)
-  const int nkt = a.nkb * a.segs;                                   // k-blocks per item
+  const int nkt = a.nkb * a.segs;                                   // recurrent k-blocks per item
+  const int pre = FUSE ? a.pre_nkb : 0;                             // input-projection k-blocks per item (before them)
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_h);
     tma_prefetch_desc(&tm_w);
     if (MC) tma_prefetch_desc(&tm_h64);
+    if (FUSE) tma_prefetch_desc(&tm_x);
     if (a.diag != nullptr && blockIdx.x == 0) {  // SM clock of this launch = d(clock64) / d(globaltimer)
       unsigned long long g;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
@@ -182,10 +197,20 @@ __device__ __forceinline__ void lstm_layer_body(const CUtensorMap& tm_h, const C
       for (long long n = pair; n < total && !aborted(ab); n += P, ++k) {
         const int t = static_cast<int>(n / C);
         const int g = static_cast<int>(n - static_cast<long long>(t) * C) / tiles;
+        const int row0 = t * b_pad + g * 256 + static_cast<int>(crank) * 128;  // ring slot t = h_{t-1} (chunk-local)
+        if constexpr (FUSE) {
+          // x_t = slot t+1 of the previous layer's ring (complete before this launch): no dependency on the step counters
+          for (int kb = 0; kb < pre; ++kb) {
+            mbar_wait(&empty[stage], phase ^ 1, ab);
+            if (crank == 0) mbar_arrive_expect_tx(&full[stage], 2 * a_bytes);
+            else mbar_arrive_remote(&full[stage], leader);
+            tma_load_2d_pair(ring + stage * stage_bytes, &tm_x, &full[stage], kb * 64, row0 + b_pad, kEvictNormal);
+            if (++stage == kLStages) { stage = 0; phase ^= 1; }
+          }
+        }
         wait_seq_ge(cready, static_cast<uint32_t>(k + 1), ab);  // the watcher (warp 2) has seen counter (t-1, g)
         if (t > 0) fence_proxy_async();  // h_{t-1} was written through the generic proxy, TMA reads it
         IE_TRACE(0, k);
-        const int row0 = t * b_pad + g * 256 + static_cast<int>(crank) * 128;  // ring slot t = h_{t-1} (chunk-local)
         for (int kb = 0; kb < nkt; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1, ab);
           if (crank == 0) mbar_arrive_expect_tx(&full[stage], 2 * a_bytes);
@@ -214,6 +239,18 @@ __device__ __forceinline__ void lstm_layer_body(const CUtensorMap& tm_h, const C
       for (long long n = pair; n < total && !aborted(ab); n += P, ++k) {
         const int t = static_cast<int>(n / C);
         const int g = static_cast<int>(n - static_cast<long long>(t) * C) / tiles;
+        if constexpr (FUSE) {
+          // x_t of the pair's NEXT item streams from DRAM (the previous layer's ring is far larger than the L2): pull this
+          // CTA's rows into the L2 one item ahead, so the operand ring sees L2 latency (13 column tiles share each x tile;
+          // the redundant prefetches of the other twelve pairs are L2 hits)
+          const long long n2 = n + P;
+          if (a.prefetch_x && n2 < total) {
+            const int t2 = static_cast<int>(n2 / C);
+            const int g2 = static_cast<int>(n2 - static_cast<long long>(t2) * C) / tiles;
+            const int rowx = (t2 + 1) * b_pad + g2 * 256 + static_cast<int>(crank) * 128;
+            for (int kb = 0; kb < pre; ++kb) tma_prefetch_2d(&tm_x, kb * 64, rowx);
+          }
+        }
         if (t > 0) wait_flag_ge_relaxed(a.step_done + (t - 1) * ng + g, batch_ctas, ab);  // ends with a gpu-scope fence
         st_release_cta(cready, static_cast<uint32_t>(k + 1));
       }
@@ -226,11 +263,11 @@ __device__ __forceinline__ void lstm_layer_body(const CUtensorMap& tm_h, const C
       for (long long n = pair; n < total && !aborted(ab); n += P) {
         const int j = static_cast<int>(n % C) % tiles;
         const int wrow0 = (2 * j + static_cast<int>(crank)) * kLHalfRows;  // slices are [cta][unit][gate], 128 rows each
-        for (int kb = 0; kb < nkt; ++kb) {
+        for (int kb = 0; kb < pre + nkt; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1, ab);
           if (crank == 0) mbar_arrive_expect_tx(&full[stage], 2 * w_bytes);
           else mbar_arrive_remote(&full[stage], leader);
-          const int seg = kb / a.nkb, r = kb - seg * a.nkb;            // split-bf16: [W_hi | W_hi | W_lo]
+          const int seg = FUSE ? 0 : kb / a.nkb, r = kb - seg * a.nkb;  // split-bf16: [W_hi | W_hi | W_lo]; FUSE: [W_ih | W_hh]
           tma_load_2d_pair(ring + stage * stage_bytes + a_bytes, &tm_w, &full[stage], (seg == 2 ? a.kh_pad : 0) + r * 64,
                            wrow0, kEvictLast);
           if (++stage == kLStages) { stage = 0; phase ^= 1; }
@@ -254,10 +291,11 @@ __device__ __forceinline__ void lstm_layer_body(const CUtensorMap& tm_h, const C
           mbar_wait(&tempty[slot], static_cast<uint32_t>(((k >> 1) - 1) & 1), ab);
           IE_TRACE_VAL(11, k, trace ? clock64() - c0 : 0);
         }
-        for (int kb = 0; kb < nkt; ++kb) {
+        for (int kb = 0; kb < pre + nkt; ++kb) {
           const long long c0 = trace ? clock64() : 0;
           mbar_wait(&full[st], ph, ab);
-          if (kb == 0) { IE_TRACE(2, k); t_first = trace ? clock64() : 0; }
+          if (kb == 0) t_first = trace ? clock64() : 0;
+          if (kb == pre) IE_TRACE(2, k);                               // first h_{t-1} stage landed
           else if (trace) wa += clock64() - c0;
           tc_fence_after();
           const uint64_t da = umma_desc_sw128(ring_base + st * stage_bytes);
@@ -300,9 +338,12 @@ __device__ __forceinline__ void lstm_layer_body(const CUtensorMap& tm_h, const C
       // all of this thread's Gx (4 chunks x 4 units x 4 gates) and c are loaded while the MMAs still run
       constexpr int kCh = 4;
       constexpr int kGW = GXBF ? 8 : 16;   // 32-bit words of Gx per chunk
-      uint32_t gxw[kCh][kGW];
+      [[maybe_unused]] uint32_t gxw[FUSE ? 1 : kCh][FUSE ? 1 : kGW];
       float4 cr[kCh];
-      if constexpr (GXBF) {
+      [[maybe_unused]] const float4* bias4 = FUSE ? reinterpret_cast<const float4*>(a.bias + 4ll * unit0) : nullptr;
+      if constexpr (FUSE) {
+        // nothing to stream: the bias (the same 64 floats for every row of the warp) is read chunk by chunk below
+      } else if constexpr (GXBF) {
         const __half* gxp = reinterpret_cast<const __half*>(a.gx) + grow * (4ll * a.out_pad) + 4ll * unit0;
 #pragma unroll
         for (int ch = 0; ch < kCh; ++ch) ldg_stream8_b32(gxp + ch * 16, &gxw[ch][0]);
@@ -346,7 +387,10 @@ __device__ __forceinline__ void lstm_layer_body(const CUtensorMap& tm_h, const C
         tmem_ld16(taddr + ch * 16, r);
         tmem_ld_wait();
         float4 gx4[4];
-        if constexpr (GXBF) {
+        if constexpr (FUSE) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) gx4[u] = __ldg(bias4 + ch * 4 + u);
+        } else if constexpr (GXBF) {
           gx_unpack_f16(gxw[ch], gx4);
         } else {
 #pragma unroll
@@ -427,25 +471,37 @@ thread_local int g_last_max_pairs = 0;   // result of the last check_only query 
 template <bool TOK, bool GXBF, bool POOL>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kLThreads, 1)
 lstm_layer_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ CUtensorMap tm_w,
-                  const __grid_constant__ CUtensorMap tm_h64, const __grid_constant__ KArgs a) {
-  lstm_layer_body<TOK, GXBF, POOL, false>(tm_h, tm_w, tm_h64, a);
+                  const __grid_constant__ CUtensorMap tm_h64, const __grid_constant__ CUtensorMap tm_x,
+                  const __grid_constant__ KArgs a) {
+  lstm_layer_body<TOK, GXBF, POOL, false, false>(tm_h, tm_w, tm_h64, tm_x, a);
+}
+
+// input projection fused into the K loop (the last layer by default; see FUSE above)
+template <bool POOL>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kLThreads, 1)
+lstm_layer_fused_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ CUtensorMap tm_w,
+                        const __grid_constant__ CUtensorMap tm_h64, const __grid_constant__ CUtensorMap tm_x,
+                        const __grid_constant__ KArgs a) {
+  lstm_layer_body<false, true, POOL, false, true>(tm_h, tm_w, tm_h64, tm_x, a);
 }
 
 template <bool TOK>
 __global__ void __launch_bounds__(kLThreads, 1)
 lstm_layer_mc_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ CUtensorMap tm_w,
-                     const __grid_constant__ CUtensorMap tm_h64, const __grid_constant__ KArgs a) {
-  lstm_layer_body<TOK, true, false, true>(tm_h, tm_w, tm_h64, a);
+                     const __grid_constant__ CUtensorMap tm_h64, const __grid_constant__ CUtensorMap tm_x,
+                     const __grid_constant__ KArgs a) {
+  lstm_layer_body<TOK, true, false, true, false>(tm_h, tm_w, tm_h64, tm_x, a);
 }
 
 size_t layer_smem_bytes() {
   return 1024 + static_cast<size_t>(kLStages) * (128 * 64 * 2 + kLHalfRows * 64 * 2) + (2 * kLStages + 4) * 8 + 32;
 }
 
-template <bool TOK, bool GXBF, bool POOL, bool MC>
+template <bool TOK, bool GXBF, bool POOL, bool MC, bool FUSE = false>
 cudaError_t launch_layer_t(const LstmLayerArgs& a, int pairs, int tiles, cudaStream_t stream) {
-  void (*kfn)(CUtensorMap, CUtensorMap, CUtensorMap, KArgs);
+  void (*kfn)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, KArgs);
   if constexpr (MC) kfn = lstm_layer_mc_kernel<TOK>;
+  else if constexpr (FUSE) kfn = lstm_layer_fused_kernel<POOL>;
   else kfn = lstm_layer_kernel<TOK, GXBF, POOL>;
   const size_t smem = layer_smem_bytes();
   // function attributes are per device: set on every launch (cheap), never cached in a process-wide flag
@@ -483,7 +539,7 @@ cudaError_t launch_layer_t(const LstmLayerArgs& a, int pairs, int tiles, cudaStr
     return max_clusters >= a.num_sms / 2 ? cudaSuccess : cudaErrorCooperativeLaunchTooLarge;
   }
   KArgs k{};
-  k.gx = a.gx; k.tok = a.tok; k.cstate = a.c; k.y = a.y; k.raw = a.raw;
+  k.gx = a.gx; k.tok = a.tok; k.bias = a.bias; k.pre_nkb = FUSE ? a.pre_nkb : 0; k.prefetch_x = a.prefetch_x; k.cstate = a.c; k.y = a.y; k.raw = a.raw;
   k.pool_sum = a.pool_sum; k.pool_max = a.pool_max; k.pool_last = a.pool_last; k.lengths = a.lengths;
   k.step_done = a.step_done; k.abort_flag = a.abort_flag;
   k.spin_limit = a.spin_limit > 0 ? a.spin_limit : kSpinLimitDefault;
@@ -497,7 +553,7 @@ cudaError_t launch_layer_t(const LstmLayerArgs& a, int pairs, int tiles, cudaStr
     ++na;
   }
   cfg.numAttrs = na;
-  return cudaLaunchKernelEx(&cfg, kfn, a.tm_h, a.tm_w, a.tm_h64, k);
+  return cudaLaunchKernelEx(&cfg, kfn, a.tm_h, a.tm_w, a.tm_h64, FUSE ? a.tm_x : a.tm_h, k);
 }
 
 }  // namespace
@@ -506,7 +562,8 @@ int lstm_layer_max_pairs() { return g_last_max_pairs; }
 
 // multicast needs sibling pairs to hold items of the same (timestep, batch): tiles (hence C and the item total) even
 bool lstm_layer_mc_ok(const LstmLayerArgs& a) {
-  return a.mc != 0 && a.gx_bf16 && a.pool_sum == nullptr && a.segs == 1 && (a.n_cta / 2) % 2 == 0 && a.mc_pairs >= 2;
+  return a.mc != 0 && a.gx_bf16 && a.pool_sum == nullptr && a.pre_nkb == 0 && a.segs == 1 && (a.n_cta / 2) % 2 == 0 &&
+         a.mc_pairs >= 2;
 }
 
 int lstm_layer_pairs(const LstmLayerArgs& a) {
@@ -527,6 +584,11 @@ cudaError_t launch_lstm_layer(const LstmLayerArgs& a, cudaStream_t stream) {
   if (pairs < 1) return cudaErrorInvalidValue;
   const bool tok = a.tok != nullptr;  // layer 0 reading its input projection from the per-token table
   const bool pool = a.pool_sum != nullptr;
+  if (a.pre_nkb > 0) {  // input projection fused into the K loop: tm_w covers [W_ih | W_hh], tm_x the previous layer's ring
+    if (a.check_only || tok || a.segs != 1 || a.bias == nullptr) return cudaErrorInvalidValue;
+    return pool ? launch_layer_t<false, true, true, false, true>(a, pairs, tiles, stream)
+                : launch_layer_t<false, true, false, false, true>(a, pairs, tiles, stream);
+  }
   if (!a.check_only && lstm_layer_mc_ok(a))
     return tok ? launch_layer_t<true, true, false, true>(a, pairs, tiles, stream)
                : launch_layer_t<false, true, false, true>(a, pairs, tiles, stream);

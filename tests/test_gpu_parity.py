@@ -202,7 +202,7 @@ def test_edge_cases_and_errors(r4):
 
 
 KNOBS = ("IE_SEQ", "IE_COOP", "IE_EMB_PROJ", "IE_GX_BF16", "IE_BATCHES", "IE_CHUNK_T", "IE_FAST_MATH", "IE_MC",
-         "IE_SPIN_LIMIT_MS", "IE_DEBUG_FAULT")
+         "IE_SPIN_LIMIT_MS", "IE_DEBUG_FAULT", "IE_FUSE_LAST")
 
 
 def _make(cfg, weights, monkeypatch, env=None, flags=0):
@@ -223,14 +223,21 @@ def _make(cfg, weights, monkeypatch, env=None, flags=0):
                                    {"IE_MC": 1}, {"IE_MC": 0}, {"IE_MC": 1, "IE_BATCHES": 4, "IE_CHUNK_T": 7},
                                    {"IE_GX_BF16": 0, "_base": {"IE_GX_BF16": 0, "IE_SEQ": 0, "IE_CHUNK_T": 3}},
                                    {"IE_FAST_MATH": 0, "_base": {"IE_FAST_MATH": 0, "IE_SEQ": 0}},
-                                   {"IE_BATCHES": 12, "IE_MC": 1}])
+                                   {"IE_BATCHES": 12, "IE_MC": 1}, {"IE_FUSE_LAST": 0, "_base": {"IE_FUSE_LAST": 0, "IE_SEQ": 0}},
+                                   {"IE_FUSE_LAST": 0, "IE_BATCHES": 2, "IE_CHUNK_T": 6, "_base": {"IE_FUSE_LAST": 0}}])
 def test_every_path_gives_identical_bits(knobs, monkeypatch):
     """One persistent kernel (csrc/lstm_layer.cu) + one fallback (csrc/lstm.cu, IE_SEQ=0) share the cell arithmetic of
     csrc/lstm_common.cuh; the per-token input-projection table is the same GEMM on the same operands as gather + GEMM;
     batches per launch, time chunking and the cooperative attribute change the schedule, not the per-row arithmetic.
-    All of them must reproduce the default path bit for bit, pooled and raw."""
+    All of them must reproduce the default path bit for bit, pooled and raw.  The one exception by construction: the
+    persistent kernel fuses the LAST layer's input projection into its K loop (f32 sum, no fp16 Gx), which the
+    per-timestep fallback cannot -- comparisons with the fallback run both sides with IE_FUSE_LAST=0
+    (test_fused_last_layer covers the fused form)."""
     knobs = dict(knobs)
     base_env = knobs.pop("_base", None)
+    if knobs.get("IE_SEQ") == 0 or (base_env or {}).get("IE_SEQ") == 0:
+        knobs["IE_FUSE_LAST"] = 0
+        base_env = dict(base_env or {}, IE_FUSE_LAST=0)
     cfg = (3, 96, 200, 500)
     weights = R.make_encoder(7, cfg[3], cfg[1], cfg[2], cfg[0]).export_weights()
     base = _make(cfg, weights, monkeypatch, base_env)
@@ -243,6 +250,36 @@ def test_every_path_gives_identical_bits(knobs, monkeypatch):
             np.testing.assert_array_equal(exp.raw_features(ids), base.raw_features(ids))
     base.close()
     exp.close()
+
+
+def test_fused_last_layer(monkeypatch):
+    """The last layer's input projection inside the recurrent K loop (default) against the hoisted GEMM form
+    (IE_FUSE_LAST=0) and against the oracle: the fused sum W_ih x + W_hh h + b never leaves f32, so it must be at least as
+    close to the oracle as the hoisted form, and the two forms agree to fp16-Gx rounding.  Shapes: padded dims (K of the
+    previous layer 200 -> 256), 1..5 batches per launch, time chunks, raw features."""
+    cfg = (3, 96, 200, 500)
+    ref = R.make_encoder(7, cfg[3], cfg[1], cfg[2], cfg[0], scale=2.0)
+    weights = ref.export_weights()
+    fused = _make(cfg, weights, monkeypatch)
+    hoist = _make(cfg, weights, monkeypatch, {"IE_FUSE_LAST": 0})
+    chunked = _make(cfg, weights, monkeypatch, {"IE_CHUNK_T": 4, "IE_BATCHES": 2})
+    for B, T in ((1, 9), (130, 19), (700, 23), (1280, 6)):
+        docs = R.synthetic_ids(B, T, seed=B + T, vocab_sz=cfg[3], min_len=1)
+        ids, lengths = _pad(docs, T)
+        a, b = fused.encode_ids(ids, lengths), hoist.encode_ids(ids, lengths)
+        assert not np.array_equal(a, b)                      # really two different code paths
+        np.testing.assert_allclose(a, b, rtol=0, atol=3e-3)
+        np.testing.assert_array_equal(chunked.encode_ids(ids, lengths), a)
+        sel = np.arange(min(B, 32))
+        want = R.encode_padded(ref, ids[sel], lengths[sel])
+        ma, mb = R.parity_metrics(a[sel], want), R.parity_metrics(b[sel], want)
+        assert ma["min_cosine"] >= COS_MIN and ma["rel_l2"] <= REL_L2_MAX_SCALED, ma
+        assert ma["rel_l2"] <= 1.25 * mb["rel_l2"], (ma, mb)
+        if B <= 130:
+            np.testing.assert_allclose(fused.raw_features(ids), hoist.raw_features(ids), rtol=0, atol=3e-3)
+            np.testing.assert_array_equal(fused.raw_features(ids), chunked.raw_features(ids))
+    for e in (fused, hoist, chunked):
+        e.close()
 
 
 def test_shape_sweep_vs_oracle_and_bulk_pipeline(monkeypatch):
