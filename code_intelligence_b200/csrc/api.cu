@@ -107,7 +107,6 @@ struct ie_encoder {
   int cooperative = 1;     // launch attribute (IE_COOP=0: plain launch, co-residency by the occupancy check only)
   int use_mc = 0;          // IE_MC=1: sibling CTA pairs share h tiles by TMA multicast (clusters of four)
   int mc_pairs = 0;        // pairs co-resident in clusters of four
-  int fuse_prefetch = 1;   // fused last layer: L2 prefetch of the next item's x tiles (IE_FUSE_PREFETCH)
   int batches = 5;         // batches of 256 rows one launch takes (IE_BATCHES, <= kMaxBatches)
   int fuse_last = 1;       // the last layer's input projection rides its recurrent K loop (lstm_layer.cu FUSE) instead of a
                            // hoisted GEMM + Gx round trip (IE_FUSE_LAST=0: hoisted like the other layers)
@@ -472,7 +471,7 @@ int run_encoder(ie_encoder* h, const int64_t* ids, const int32_t* lengths, int B
         CK(cudaMemsetAsync(h->step_done.p, 0, static_cast<size_t>(Tc) * ng * sizeof(unsigned), s));
         ie::LstmLayerArgs q{};
         q.tm_h = tm_h; q.tm_w = tm_w; q.tm_h64 = tm_h64; q.mc = h->use_mc; q.mc_pairs = h->mc_pairs;
-        q.tm_x = tm_x; q.pre_nkb = fused ? L.kin_pad / 64 : 0; q.bias = L.bias.as<float>(); q.prefetch_x = h->fuse_prefetch;
+        q.tm_x = tm_x; q.pre_nkb = fused ? L.kin_pad / 64 : 0; q.bias = L.bias.as<float>();
         q.gx = from_table ? h->proj.p : h->gx.p;
         q.tok = from_table ? h->tok.as<int>() : nullptr;
         q.c = cstate; q.y = ybuf;
@@ -631,7 +630,6 @@ int ie_encoder_create(const ie_config* cfg, ie_encoder** out) {
   if (const char* v = getenv("IE_GX_BF16")) { if (h->segs == 1) h->gx_bf16 = atoi(v); }
   if (const char* v = getenv("IE_FAST_MATH")) { if (h->segs == 1) h->gate_mode = atoi(v) ? 2 : 1; }
   if (const char* v = getenv("IE_FUSE_LAST")) h->fuse_last = atoi(v);
-  if (const char* v = getenv("IE_FUSE_PREFETCH")) h->fuse_prefetch = atoi(v);
   if (const char* v = getenv("IE_BATCHES")) h->batches = std::min(ie::kMaxBatches, std::max(1, atoi(v)));
   if (const char* v = getenv("IE_SPIN_LIMIT_MS")) h->spin_limit = static_cast<long long>(atof(v) * 1.9e6);
   if (const char* v = getenv("IE_DEBUG_FAULT")) h->fault = atoi(v);

@@ -69,7 +69,6 @@ struct LstmLayerArgs {
                            // x_t W_ih^T precede the recurrent ones; tm_w then covers [W_ih | W_hh] (inner kin_pad + kh_pad),
                            // gx is unused and `bias` (b_ih + b_hh, permuted like the weight rows) is added instead
   const float* bias;
-  int prefetch_x;          // fused form: L2 prefetch of the next item's x tiles (default on; IE_FUSE_PREFETCH=0)
   int mc;                  // 1: clusters of two CTA pairs share every h tile by TMA multicast (needs an even number of tiles)
   int mc_pairs;            // CTA pairs that can be co-resident in clusters of four (lstm_layer_max_pairs() of a check_only query)
   const void* gx;

@@ -83,7 +83,6 @@ struct KArgs {
   long long* diag;
   int T, t0, T_total, ng, tiles, out_pad, nkb, segs, kh_pad, gate_mode, trace_items, fault;
   int pre_nkb;           // FUSE: k-blocks of the input projection that precede the recurrent ones in every item
-  int prefetch_x;        // FUSE: L2 prefetch of the next item's x tiles by the watcher thread
 };
 
 // TOK: Gx rows are rows of the per-token input-projection table; GXBF: Gx / table stored as fp16 (f32 otherwise);
@@ -239,18 +238,6 @@ __device__ __forceinline__ void lstm_layer_body(const CUtensorMap& tm_h, const C
       for (long long n = pair; n < total && !aborted(ab); n += P, ++k) {
         const int t = static_cast<int>(n / C);
         const int g = static_cast<int>(n - static_cast<long long>(t) * C) / tiles;
-        if constexpr (FUSE) {
-          // x_t of the pair's NEXT item streams from DRAM (the previous layer's ring is far larger than the L2): pull this
-          // CTA's rows into the L2 one item ahead, so the operand ring sees L2 latency (13 column tiles share each x tile;
-          // the redundant prefetches of the other twelve pairs are L2 hits)
-          const long long n2 = n + P;
-          if (a.prefetch_x && n2 < total) {
-            const int t2 = static_cast<int>(n2 / C);
-            const int g2 = static_cast<int>(n2 - static_cast<long long>(t2) * C) / tiles;
-            const int rowx = (t2 + 1) * b_pad + g2 * 256 + static_cast<int>(crank) * 128;
-            for (int kb = 0; kb < pre; ++kb) tma_prefetch_2d(&tm_x, kb * 64, rowx);
-          }
-        }
         if (t > 0) wait_flag_ge_relaxed(a.step_done + (t - 1) * ng + g, batch_ctas, ab);  // ends with a gpu-scope fence
         st_release_cta(cready, static_cast<uint32_t>(k + 1));
       }
@@ -359,15 +346,17 @@ __device__ __forceinline__ void lstm_layer_body(const CUtensorMap& tm_h, const C
       if (lane == 0) wait_seq_ge(cready, static_cast<uint32_t>(k + 1), ab);
       __syncwarp();
 #pragma unroll
-      for (int ch = 0; ch < kCh; ++ch)
-        cr[ch] = (tg == 0) ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldcg(reinterpret_cast<const float4*>(cp) + ch);
+      for (int ch = 0; ch < kCh; ch += 2) {   // full-sector (256-bit) loads
+        if (tg == 0) cr[ch] = cr[ch + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        else ldg_cg8(cp + ch * 4, cr[ch], cr[ch + 1]);
+      }
       // last layer: the running max travels like c (L2, loaded before the accumulator is ready); the sum is an L2 reduction
       [[maybe_unused]] float4 pm[POOL ? kCh : 1];
       [[maybe_unused]] const long long po = static_cast<long long>(brow) * a.out_pad + unit0;
       if constexpr (POOL) {
         if (tg > 0 && tg < len) {
 #pragma unroll
-          for (int ch = 0; ch < kCh; ++ch) pm[ch] = __ldcg(reinterpret_cast<const float4*>(a.pool_max + po) + ch);
+          for (int ch = 0; ch < kCh; ch += 2) ldg_cg8(a.pool_max + po + ch * 4, pm[ch], pm[ch + 1]);
         }
       }
       if (threadIdx.x == 128) IE_TRACE(7, k);
@@ -539,7 +528,7 @@ cudaError_t launch_layer_t(const LstmLayerArgs& a, int pairs, int tiles, cudaStr
     return max_clusters >= a.num_sms / 2 ? cudaSuccess : cudaErrorCooperativeLaunchTooLarge;
   }
   KArgs k{};
-  k.gx = a.gx; k.tok = a.tok; k.bias = a.bias; k.pre_nkb = FUSE ? a.pre_nkb : 0; k.prefetch_x = a.prefetch_x; k.cstate = a.c; k.y = a.y; k.raw = a.raw;
+  k.gx = a.gx; k.tok = a.tok; k.bias = a.bias; k.pre_nkb = FUSE ? a.pre_nkb : 0; k.cstate = a.c; k.y = a.y; k.raw = a.raw;
   k.pool_sum = a.pool_sum; k.pool_max = a.pool_max; k.pool_last = a.pool_last; k.lengths = a.lengths;
   k.step_done = a.step_done; k.abort_flag = a.abort_flag;
   k.spin_limit = a.spin_limit > 0 ? a.spin_limit : kSpinLimitDefault;

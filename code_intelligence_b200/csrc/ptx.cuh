@@ -135,11 +135,6 @@ __device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap
       : "memory");
 }
 
-// 2-D tile global -> L2 only (no shared-memory destination, no completion): warms the L2 for a later tma_load of the box
-__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* m, int32_t c0, int32_t c1) {
-  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(m), "r"(c0), "r"(c1) : "memory");
-}
-
 // 2-D tiled store shared -> global (bulk async group); out-of-range parts of the box are clipped by the tensor map
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int32_t c0, int32_t c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
@@ -400,6 +395,16 @@ __device__ __forceinline__ void ldg_stream8(const float* p, float4& a, float4& b
   asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
                : "l"(p));
+}
+
+// 256-bit coherent load that bypasses L1 (state written by another SM of the same launch: c, running max).  One full
+// 32-byte sector per request -- two 128-bit ld.cg of the same sector are two requests and move the sector twice
+// (ncu: 6.4 GB of the recurrent kernel's 25.7 GB of LSU reads per launch were the second halves of c sectors).
+__device__ __forceinline__ void ldg_cg8(const float* p, float4& a, float4& b) {
+  asm volatile("ld.global.cg.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+               : "l"(p)
+               : "memory");
 }
 
 // same load into eight 32-bit registers (f32 bits or packed bf16 pairs)

@@ -24,7 +24,7 @@ for i, d in enumerate(docs):
     ids[i, :len(d)] = d
 lengths = np.array([len(d) for d in docs], dtype=np.int32)
 want = R.encode_padded(ref, ids, lengths)
-for name, env in (("persistent", {}), ("fallback+gather", {"IE_SEQ": "0", "IE_EMB_PROJ": "0"}), ("chunked", {"IE_CHUNK_T": "2"})):
+for name, env in (("persistent (last layer fused)", {}), ("persistent, hoisted last layer", {"IE_FUSE_LAST": "0"}), ("fallback+gather", {"IE_SEQ": "0", "IE_EMB_PROJ": "0"}), ("chunked", {"IE_CHUNK_T": "2"})):
     os.environ.update(env)
     enc = IssueEncoder(*cfg, 1, 0).load_weights(*weights)
     for k in env:
