@@ -155,7 +155,9 @@ struct ie_mlp {
   };
   std::vector<L> layers;
   DevBuf xf, act[2], probs;
+  DevBuf xb;                // bf16 copy of one row chunk of X
   long long act_ld = 0;
+  int chunk_dev = 1 << 18;  // rows per pass in device-pointer mode (IE_MLP_CHUNK at create time)
   cudaStream_t own_stream = nullptr;
   std::mutex mu;
 };
@@ -829,6 +831,7 @@ int ie_mlp_create(int32_t n_layers, const int32_t* dims, int32_t device, ie_mlp*
     ld = std::max<long long>(ld, round_up(std::max(L.n_pad, L.k_pad), 64));
   }
   m->act_ld = ld;
+  if (const char* v = getenv("IE_MLP_CHUNK")) m->chunk_dev = static_cast<int>(round_up(std::max(256, atoi(v)), 256));
   e = cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) { delete m; return cuda_fail(e, "cudaStreamCreate"); }
   *out = m;
@@ -869,28 +872,39 @@ int ie_mlp_predict_proba(ie_mlp* m, const float* X, int32_t n, float* probs, int
   cudaStream_t s = (stream || dev) ? static_cast<cudaStream_t>(stream) : m->own_stream;
   const int nl = static_cast<int>(m->layers.size());
   const int d_in = m->dims[0], n_labels = m->dims[nl];
-  const int chunk = 1 << 16;
+  // rows per pass: host buffers are staged through a 2^16-row device buffer; device pointers take chunk_dev rows
+  int chunk = dev ? m->chunk_dev : (1 << 16);
+  chunk = static_cast<int>(std::min<long long>(chunk, round_up(n, 256)));
   const ie_mlp::L& LL = m->layers[nl - 1];
+  // the last GEMM writes straight into the caller's array when its row pitch is a legal store width
+  const bool direct_out = dev && n_labels % 16 == 0 && n_labels == LL.n_pad;
+  // (Converting chunk k+1 on a side stream under the GEMMs of chunk k was measured: 6.79 vs 6.84 ms per 2^20 rows at
+  // D_in = 2400 -- the HBM-bound convert pass and the tensor-bound GEMMs share the board's power budget, not only the SMs;
+  // profiles/README.md.)
   CK(m->act[0].reserve(static_cast<size_t>(chunk) * m->act_ld * sizeof(__nv_bfloat16), true));
   CK(m->act[1].reserve(static_cast<size_t>(chunk) * m->act_ld * sizeof(__nv_bfloat16), true));
-  CK(m->probs.reserve(static_cast<size_t>(chunk) * LL.n_pad * sizeof(float)));
+  CK(m->xb.reserve(static_cast<size_t>(chunk) * m->act_ld * sizeof(__nv_bfloat16), true));
+  if (!direct_out) CK(m->probs.reserve(static_cast<size_t>(chunk) * LL.n_pad * sizeof(float)));
   if (!dev) CK(m->xf.reserve(static_cast<size_t>(chunk) * d_in * sizeof(float)));
   for (long long r0 = 0; r0 < n; r0 += chunk) {
     const int rows = static_cast<int>(std::min<long long>(chunk, n - r0));
-    const int m_pad = static_cast<int>(round_up(rows, 128));
+    // whole M = 256 tiles when there are enough of them for the CTA-pair GEMM (rows past `rows` hold stale finite data
+    // and are never stored)
+    const int m_pad = static_cast<int>(rows >= 256 * 40 ? round_up(rows, 256) : round_up(rows, 128));
     const float* xsrc = X + r0 * d_in;
     if (!dev) {
       CK(cudaMemcpyAsync(m->xf.p, xsrc, static_cast<size_t>(rows) * d_in * sizeof(float), cudaMemcpyHostToDevice, s));
       xsrc = m->xf.as<float>();
     }
-    // f32 -> bf16, K padded with zeros (rows beyond `rows` keep stale finite data; they are never stored)
-    CK(ie::launch_convert_rows(xsrc, d_in, d_in, nullptr, rows, m->act[0].as<__nv_bfloat16>(), m->act_ld, 0, s));
+    __nv_bfloat16* xbuf = m->xb.as<__nv_bfloat16>();
+    CK(ie::launch_convert_rows(xsrc, d_in, d_in, nullptr, rows, xbuf, m->act_ld, 0, s));   // f32 -> bf16, K padded with zeros
+    const __nv_bfloat16* cur_in = xbuf;
     int cur = 0;
     for (int l = 0; l < nl; ++l) {
       const ie_mlp::L& L = m->layers[l];
       const bool last = (l == nl - 1);
       ie::GemmArgs g{};
-      g.a = m->act[cur].as<__nv_bfloat16>();
+      g.a = cur_in;
       g.lda = m->act_ld;
       g.b = L.w.as<__nv_bfloat16>();
       g.ldb = L.k_pad;
@@ -903,22 +917,24 @@ int ie_mlp_predict_proba(ie_mlp* m, const float* X, int32_t n, float* probs, int
       g.bn = L.bn;
       g.num_sms = m->num_sms;
       if (last) {
-        g.d = m->probs.p;
+        g.d = direct_out ? static_cast<void*>(probs + r0 * n_labels) : m->probs.p;
         g.ldd = L.n_pad;
         g.act = 2;
         g.out_bf16 = 0;
       } else {
-        g.d = m->act[cur ^ 1].p;
+        g.d = m->act[cur].p;
         g.ldd = m->act_ld;
         g.act = 1;
         g.out_bf16 = 1;
       }
       CK(ie::launch_gemm_bf16(g, s));
+      cur_in = m->act[cur].as<__nv_bfloat16>();
       cur ^= 1;
     }
-    CK(cudaMemcpy2DAsync(probs + r0 * n_labels, static_cast<size_t>(n_labels) * sizeof(float), m->probs.p,
-                         static_cast<size_t>(LL.n_pad) * sizeof(float), static_cast<size_t>(n_labels) * sizeof(float),
-                         rows, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
+    if (!direct_out)
+      CK(cudaMemcpy2DAsync(probs + r0 * n_labels, static_cast<size_t>(n_labels) * sizeof(float), m->probs.p,
+                           static_cast<size_t>(LL.n_pad) * sizeof(float), static_cast<size_t>(n_labels) * sizeof(float),
+                           rows, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
     if (!dev) CK(cudaStreamSynchronize(s));  // xf is reused by the next chunk
   }
   return IE_OK;
@@ -968,7 +984,7 @@ void ie_mlp_destroy(ie_mlp* m) {
   cudaSetDevice(m->device);
   cudaDeviceSynchronize();
   for (auto& L : m->layers) { L.w.release(); L.b.release(); }
-  m->xf.release(); m->act[0].release(); m->act[1].release(); m->probs.release();
+  m->xf.release(); m->act[0].release(); m->act[1].release(); m->probs.release(); m->xb.release();
   if (m->own_stream) cudaStreamDestroy(m->own_stream);
   delete m;
 }
