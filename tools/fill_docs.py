@@ -18,11 +18,11 @@ def tf(flop, ms): return flop / ms / 1e9
 L = [("layer 0 (800→2400): table lookup + recurrence", None, ph["steps"][0], 2.0*rows*512*9600*2400, mhz["steps"][0], None),
      ("layer 1 (2400→2400): GEMM + recurrence", ph["gemm"][1], ph["steps"][1], 2.0*rows*512*9600*2400, mhz["steps"][1], mhz["gemm"][1]),
      ("layer 2 (2400→2400): GEMM + recurrence", ph["gemm"][2], ph["steps"][2], 2.0*rows*512*9600*2400, mhz["steps"][2], mhz["gemm"][2]),
-     ("layer 3 (2400→800, pooled): GEMM + recurrence", ph["gemm"][3], ph["steps"][3], None, mhz["steps"][3], mhz["gemm"][3])]
+     ("layer 3 (2400→800, pooled): input projection fused into the recurrence", None, ph["steps"][3], None, mhz["steps"][3], None)]
 tab = ["| phase | input-projection GEMM | recurrent kernel | SM clock (recurrent / GEMM) |", "|---|---|---|---|"]
 for name, g, s_, fl, ms_, mg in L:
     if name.startswith("layer 3"):
-        gfl, sfl = 2.0*rows*512*3200*2400, 2.0*rows*512*3200*800
+        gfl, sfl = None, 2.0*rows*512*3200*(2400 + 800)
     else:
         gfl, sfl = fl, fl
     gcol = "—" if g is None else f"{g:.1f} ms = {tf(gfl, g):.0f} TFLOP/s"
@@ -38,7 +38,8 @@ et = ["| measurement | result |", "|---|---|",
       f"| var-len bulk encode through `bulk.encode_bulk_distributed`, 5120 issues, lengths U[64, 512], 1 GPU | {ex['bulk_varlen']['value']:.0f} issues/s, {ex['bulk_varlen']['valid_tokens_per_s']/1e6:.2f} M valid tokens/s, bit-equal to a plain single-GPU encode: {ex['bulk_varlen']['bit_equal_to_single_gpu']} |"]
 for k in ("mlp_1600", "mlp_2400"):
     m = ex[k]
-    et.append(f"| MLP head ({k[4:]}→600→600→256), 2^20 rows, device-resident | {m['rows_per_s']/1e6:.0f} M rows/s = {m['labels_per_s']/1e9:.1f} G labels/s ({m['ms']:.1f} ms); {m['hbm_gbs']:.0f} GB/s of algorithmic traffic = {m['roofline']['frac']:.2f} of the HBM roofline, {m['tflops']:.0f} TFLOP/s |")
+    rf = m['roofline']
+    et.append(f"| MLP head ({k[4:]}→600→600→256), 2^20 rows, device-resident | {m['rows_per_s']/1e6:.0f} M rows/s = {m['labels_per_s']/1e9:.1f} G labels/s ({m['ms']:.2f} ms); {m['tflops']:.0f} TFLOP/s = {rf['frac']:.2f} of the binding ({rf['bound']}) roofline; {m['hbm_gbs']:.0f} GB/s of algorithmic traffic = {rf.get('hbm_frac', rf['frac']):.2f} of the HBM roofline |")
 for dm in multi:
     et.append(f"| {dm['n_gpus']} GPUs: `value` / `e2e` (bulk API) / var-len strong scaling | {dm['value']:.0f} / {dm['e2e']['value']:.0f} / {dm['extra']['bulk_varlen']['value']:.0f} issues/s (bit-equal to single GPU: {dm['extra']['bulk_varlen']['bit_equal_to_single_gpu']}) |")
 cb = d1.get("cpu_baseline")
@@ -46,7 +47,8 @@ if cb:
     et.append(f"| CPU oracle on the box ({cb['cores']} threads) | {cb['value']:.1f} issues/s ({cb['sample']}) |")
 sub = {"RESULT_VALUE": f"{d1['value']:.0f}", "RESULT_E2E": f"{d1['e2e']['value']:.0f}", "RESULT_SINGLE": f"{d1['single_batch']['value']:.0f}",
        "RESULT_MS": f"{d1['ms_per_step']:.1f}", "RESULT_FRAC": f"{r['frac']:.3f}", "RESULT_WHOLE": f"{r['whole_step_frac']:.3f}",
-       "PHASE_TABLE": "\n".join(tab), "EXTRA_TABLE": "\n".join(et)}
+       "PHASE_TABLE": "\n".join(tab), "EXTRA_TABLE": "\n".join(et),
+       "BENCH_FILE": os.path.relpath(os.path.abspath(sys.argv[1]), os.path.join(ROOT, "profiles")) if "profiles" in os.path.abspath(sys.argv[1]) else sys.argv[1]}
 for name in ("profiles/README.md", "DESIGN.md", "README.md"):
     src = os.path.join(ROOT, "docs_src", name.replace("/", "__"))
     if not os.path.exists(src):
