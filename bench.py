@@ -483,6 +483,26 @@ def extras_rank0(enc, emb, layers, dev, R):
         return {"value": rows / ms * 1e3, "unit": "issues/s", "rows_per_call": rows, "ms_per_256": ms * 256 / rows,
                 "tflops": flop_tok * rows * T / ms / 1e9}
 
+    # the reference's online entry (flask_app /text, Issue_Embeddings/flask_app/app.py:49-76): ONE issue per call.  Latency of
+    # ie_encoder_encode with B = 1 (device-resident ids; the recurrence is a chain of T x L dependent steps, so this is a
+    # latency figure, not a throughput one)
+    lat = {}
+    for t_len in (128, 512):
+        ids1 = torch.randint(2, VOCAB, (1, t_len), generator=g, dtype=torch.int64).to(dev)
+        len1 = torch.full((1,), t_len, dtype=torch.int32, device=dev)
+        o1 = torch.empty((1, 3 * EMB), dtype=torch.float32, device=dev)
+        for _ in range(2):
+            enc.encode_ids_device(ids1, len1, o1)
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            enc.encode_ids_device(ids1, len1, o1)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        lat[f"T{t_len}_ms"] = e0.elapsed_time(e1) / 5
+    lat["note"] = "one issue per call (the /text endpoint's shape), device-resident ids, mean of 5 calls"
+    out["online_b1"] = lat
     # BASELINE configs[1] as written ("fp32"): split-bf16 products, f32 Gx, IEEE gates; parity in tests/test_gpu_parity.py
     e32 = IssueEncoder(N_LAYERS, EMB, HID, VOCAB, 1, dev.index, _lib.IE_CFG_FP32).load_weights(emb, layers)
     r = time_encoder(e32, e32.max_batch, 2, FLOP_PER_TOKEN)

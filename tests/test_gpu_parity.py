@@ -303,6 +303,11 @@ def test_shape_sweep_vs_oracle_and_bulk_pipeline(monkeypatch):
     docs = R.synthetic_ids(3000, 40, seed=5, vocab_sz=cfg[3], min_len=1)
     bulk_out = enc.encode_id_list(docs, bs=100)
     assert bulk_out.shape == (3000, 192)
+    # the result array owns its (page-locked) memory: a later bulk call of the same size must not overwrite it
+    keep = bulk_out.copy()
+    other = enc.encode_id_list(docs[::-1], bs=100)
+    np.testing.assert_array_equal(bulk_out, keep)
+    np.testing.assert_array_equal(other[::-1], keep)
     for i in rng.choice(3000, size=40, replace=False):
         np.testing.assert_array_equal(bulk_out[i], enc.encode_ids(docs[i][None, :])[0])
     with pytest.raises(ValueError):

@@ -36,6 +36,9 @@ et = ["| measurement | result |", "|---|---|",
       f"| fp32-accurate mode (`IE_CFG_FP32`), 1280 × 512 per call | {ex['fp32_mode']['value']:.0f} issues/s ({ex['fp32_mode']['ms_per_256']:.1f} ms per 256; {ex['fp32_mode']['tflops']:.0f} algorithmic TFLOP/s, 3× that on the tensor cores); rel-L2 vs the fp32 oracle 5.1e-6 |",
       f"| N3 (north star's literal 3-layer shape), 1280 × 512 per call | {ex['n3']['value']:.0f} issues/s ({ex['n3']['ms_per_256']:.1f} ms per 256, {ex['n3']['tflops']:.0f} TFLOP/s) |",
       f"| var-len bulk encode through `bulk.encode_bulk_distributed`, 5120 issues, lengths U[64, 512], 1 GPU | {ex['bulk_varlen']['value']:.0f} issues/s, {ex['bulk_varlen']['valid_tokens_per_s']/1e6:.2f} M valid tokens/s, bit-equal to a plain single-GPU encode: {ex['bulk_varlen']['bit_equal_to_single_gpu']} |"]
+if "online_b1" in ex:
+    ob = ex["online_b1"]
+    et.append(f"| one issue per call (the `/text` endpoint's shape, `APP:49-76`), device-resident ids | {ob['T128_ms']:.1f} ms at 128 tokens, {ob['T512_ms']:.1f} ms at 512 tokens (≈ {ob['T512_ms']/512/4*1e3:.0f} µs per layer-step: the recurrence is a chain of T × L dependent steps) |")
 for k in ("mlp_1600", "mlp_2400"):
     m = ex[k]
     rf = m['roofline']
