@@ -21,9 +21,13 @@
 //     dependency) -> 4 x tcgen05.mma per k-block into one of two TMEM accumulator slots -> 16 epilogue warps
 //     (tcgen05.ld, + Gx, gates, c_t, h_t as bf16 into slot t+1 of the hidden-state ring = next step's A operand and the
 //     next layer's GEMM input; full 32-byte sectors per store) -> gpu-scope fence + red.add on the (step, batch) counter;
-//   * the cell state moves between SMs from step to step: it lives in global memory (L2) and is read with ld.global.cg
-//     after the pair has seen the (t-1, g) counter; on the last layer the running max of the concat-pool travels the same
-//     way and the pooled sum is an L2 reduction (lstm_common.cuh), so none of them sits on the step's critical path;
+//   * the cell state moves between SMs from step to step: it lives in global memory (L2) and is read with 256-bit
+//     ld.global.cg (one request per 32-byte sector) after the pair has seen the (t-1, g) counter; on the last layer the
+//     running max of the concat-pool travels the same way and the pooled sum is an L2 reduction (lstm_common.cuh), so
+//     none of them sits on the step's critical path;
+//   * the LAST layer runs the FUSE instantiation: its input projection x_t W_ih^T (38 k-blocks that depend on no step
+//     counter) is accumulated in front of the 13 recurrent k-blocks of every item instead of by a hoisted GEMM -- the
+//     layer's 65 items per timestep cannot fill 74 pairs, and the independent k-blocks hide its step chain (see FUSE);
 //   * split-bf16 ("fp32-accurate") mode: segs = 3 runs the K loop over [h_hi | h_lo | h_hi] x [W_hi | W_hi | W_lo]
 //     (hi = bf16(x), lo = bf16(x - hi); the dropped lo*lo term is 2^-18 relative) -- same kernel, three times the MMAs.
 //
