@@ -591,6 +591,49 @@ def test_inference_wrapper_surface(tmp_path):
     np.testing.assert_array_equal(embs[1:2], w.get_pooled_features(w.process_dict(df.iloc[1].to_dict())["text"]).numpy())
     np.testing.assert_array_equal(w.df_to_emb(df), embs)
 
+    # torch checkpoints with fastai 1.0.53's module tree (SURVEY.md section 8c key list): `save_encoder` writes
+    # torch.save(model[0].state_dict()); `learn.save` writes {'model': SequentialRNN state dict ('0.' = encoder,
+    # '1.' = decoder head), 'opt': ...}.  In both the authoritative W_hh is `weight_hh_l0_raw` -- `module.weight_hh_l0`
+    # holds the last DROPPED copy of a training step, so it is filled with garbage here and must be ignored.
+    class WeightDropout(torch.nn.Module):
+        def __init__(self, module):
+            super().__init__()
+            self.module = module
+            self.weight_hh_l0_raw = torch.nn.Parameter(module.weight_hh_l0.data.clone())
+            module.weight_hh_l0.data.normal_()
+
+    class EmbeddingDropout(torch.nn.Module):
+        def __init__(self, emb):
+            super().__init__()
+            self.emb = emb
+
+    class AwdLstmTree(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.encoder = torch.nn.Embedding(300, 32, padding_idx=1)
+            self.encoder.weight.data.copy_(ref.encoder.weight.data)
+            self.encoder_dp = EmbeddingDropout(self.encoder)
+            rnns = []
+            for l, r in enumerate(ref.rnns):
+                m = torch.nn.LSTM(r.input_size, r.hidden_size, 1, batch_first=True)
+                m.load_state_dict(r.state_dict())
+                rnns.append(WeightDropout(m))
+            self.rnns = torch.nn.ModuleList(rnns)
+
+    tree = AwdLstmTree()
+    keys = set(tree.state_dict().keys())
+    assert {"encoder.weight", "encoder_dp.emb.weight", "rnns.0.weight_hh_l0_raw", "rnns.1.module.weight_ih_l0",
+            "rnns.1.module.weight_hh_l0", "rnns.0.module.bias_ih_l0", "rnns.0.module.bias_hh_l0"} <= keys
+    torch.save(tree.state_dict(), tmp_path / "enc_save_encoder.pth")
+    full = {"0." + k: v for k, v in tree.state_dict().items()}
+    full["1.decoder.weight"] = tree.encoder.weight.data.clone()
+    full["1.decoder.bias"] = torch.zeros(300)
+    torch.save({"model": full, "opt": {}}, tmp_path / "learn_save.pth")
+    for name in ("enc_save_encoder.pth", "learn_save.pth"):
+        wp = InferenceWrapper(tmp_path, name, numericalizer=w._numericalizer)
+        np.testing.assert_array_equal(wp.get_pooled_features(text).numpy(), pooled.numpy())
+        wp.encoder.close()
+
 
 # ------------------------------------------------------------------------------------------------ MLP head
 @pytest.mark.parametrize("tag", ["small", "prod"])

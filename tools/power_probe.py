@@ -83,6 +83,12 @@ def run(what, seconds, T):
         enc = IssueEncoder().load_weights(*rand_weights())
         B = 256 if name == "enc256" else enc.max_batch
         ids = torch.randint(2, 60000, (B, T), dtype=torch.int64, device="cuda")
+        if os.environ.get("PROBE_IDS") == "seq":    # neighbouring rows read neighbouring rows of the per-token table
+            ids = ((torch.arange(B, device="cuda")[:, None] + 257 * torch.arange(T, device="cuda")[None, :]) % 59000 + 2).to(torch.int64)
+        elif os.environ.get("PROBE_IDS") == "zipf":  # a few hot tokens, like text
+            z = torch.distributions.Zipf(torch.tensor(1.1)).sample((B, T)) if hasattr(torch.distributions, "Zipf") else None
+            w = 1.0 / torch.arange(1, 59999, dtype=torch.float64) ** 1.1
+            ids = (torch.multinomial(w / w.sum(), B * T, replacement=True).view(B, T) + 2).to(torch.int64).cuda()
         lengths = torch.full((B,), T, dtype=torch.int32, device="cuda")
         out = torch.empty((B, enc.out_dim), dtype=torch.float32, device="cuda")
         step = lambda: enc.encode_ids_device(ids, lengths, out)
