@@ -204,6 +204,23 @@ def test_spacy_like_tokenizer_documented_cases():
         assert "".join(tok(text)).replace(" ", "") == text.replace(" ", "")
 
 
+def test_rule_tokenizer_reproduces_reference_notebook_tokens(golden_dir):
+    """Row f-1 pinned on REFERENCE OUTPUT: the token strings the reference's own pipeline (mdparse + spaCy 2.x + fastai
+    rules) printed in Issue_Embeddings/notebooks/04_Inference.ipynb:118-156 -- 41 fragments, 904 tokens (contractions,
+    possessives, version numbers, dotted identifiers, '--', '...', hyphenated words, emoji, ctrl+c, xxmaj / xxup / xxrep).
+    The notebook shows only the processed side, so each fragment's raw text is its natural detokenisation
+    (tests/golden/tokenizer_ref_notebook.json says so; three titles are also printed raw at 02_fastai_DataBunch.ipynb:118-128); fragments with mdparse markers or xxunk were cut out."""
+    import json
+    from code_intelligence_b200.inference import RuleTokenizer
+    fx = json.load(open(os.path.join(golden_dir, "tokenizer_ref_notebook.json"), encoding="utf-8"))
+    rt = RuleTokenizer(['xxunk', 'xxpad', 'xxbos', 'xxfld', 'xxmaj', 'xxup', 'xxrep', 'xxwrep'])
+    assert len(fx["fragments"]) >= 40
+    for f in fx["fragments"]:
+        unk = set(f.get("unk", []))          # words the reference's 60 000-word vocabulary did not hold
+        got = ["xxunk" if t in unk else t for t in rt.tokens(f["raw"])]
+        assert got == f["tokens"].split(" "), f["raw"]
+
+
 def test_rule_tokenizer_process_text_pipeline():
     """fastai Tokenizer.process_text restated: pre-rules -> splitter -> post-rules -> vocab lookup."""
     from code_intelligence_b200.inference import RuleTokenizer
