@@ -74,6 +74,52 @@ def mlp_fixture():
         print('mlp', tag, probs.shape, float(probs.mean()))
 
 
+def threshold_fixture():
+    """Per-label probability thresholds computed by the reference's OWN loop (MLPWrapper.find_probability_thresholds,
+    py/label_microservice/mlp.py:65-98) on preset scores: the classifier is a stand-in whose fit() does nothing and whose
+    predict_proba() returns the preset score rows, so everything after `y_pred = ...` is the reference's code (with this
+    image's sklearn precision_recall_curve).  Ties, a label without positives, labels that never qualify."""
+    sys.path.insert(0, '/root/reference/py')
+    from label_microservice.mlp import MLPWrapper
+    rng = np.random.default_rng(77)
+    out = {}
+    for tag, n, L, quant, p_thr, r_thr in [('a', 400, 12, 0, 0.7, 0.5), ('b', 1500, 30, 40, 0.6, 0.3), ('c', 97, 6, 10, 0.0, 0.0)]:
+        truth = (rng.random((n, L)) < rng.uniform(0.05, 0.5, size=L)).astype(int)
+        truth[:, 0] = 0
+        signal = rng.uniform(0.0, 3.0, size=L)
+        scores = 1.0 / (1.0 + np.exp(-(rng.standard_normal((n, L)) + signal * (truth * 2.0 - 1.0))))
+        scores = scores.astype(np.float32)
+        if quant:
+            scores = (np.round(scores * quant) / quant).astype(np.float32)
+
+        class Stub:
+            def fit(self, X, y):
+                pass
+
+            def predict_proba(self, X):
+                return scores[np.asarray(X)[:, 0].astype(int)]
+
+        w = MLPWrapper(clf=Stub(), precision_threshold=p_thr, recall_threshold=r_thr)
+        X = np.arange(n)[:, None]
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            w.find_probability_thresholds(X, truth)
+        from sklearn.model_selection import train_test_split
+        _, X_test, _, y_test = train_test_split(X, truth, test_size=0.3, random_state=1234)
+        idx = X_test[:, 0]
+        thr = np.array([np.nan if w.probability_thresholds[l] is None else w.probability_thresholds[l] for l in range(L)], dtype=np.float64)
+        out.update({f'{tag}_scores': scores[idx], f'{tag}_truth': y_test.astype(np.uint8), f'{tag}_p_thr': np.float64(p_thr),
+                    f'{tag}_r_thr': np.float64(r_thr), f'{tag}_thresholds': thr,
+                    f'{tag}_precisions': np.array([w.precisions[l] for l in range(L)], dtype=np.float64),
+                    f'{tag}_recalls': np.array([w.recalls[l] for l in range(L)], dtype=np.float64)})
+        print('thresholds', tag, int(np.isnan(thr).sum()), 'of', L, 'labels excluded')
+    np.savez_compressed(os.path.join(HERE, 'thresholds_ref.npz'), **out)
+
+
+if __name__ == '__main__' and len(sys.argv) == 2 and sys.argv[1] == 'thresholds':
+    threshold_fixture()
+
 if __name__ == '__main__' and len(sys.argv) == 1:
     encoder_fixture('encoder_tiny.npz', 2, 64, 128, 1000, 5, 9, 2, seed=11)
     encoder_fixture('encoder_pad_dims.npz', 3, 50, 70, 300, 7, 12, 1, seed=12, scale=2.0)   # dims that need padding

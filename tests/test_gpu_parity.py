@@ -678,6 +678,14 @@ def test_mlp_wrapper_matches_sklearn():
     np.testing.assert_allclose(w.predict_probabilities(Xt), clf.predict_proba(Xt), atol=5e-3)
 
 
+def test_threshold_search_on_device_vs_reference_fixture(golden_dir):
+    """ie_pr_thresholds against the thresholds / precisions / recalls the reference's own
+    MLPWrapper.find_probability_thresholds computed (tests/golden/thresholds_ref.npz, make_golden.py thresholds)."""
+    from code_intelligence_b200.mlp import pr_thresholds
+    from test_host_logic import _check_thresholds_fixture
+    _check_thresholds_fixture(pr_thresholds, golden_dir)
+
+
 def test_threshold_search_on_device_matches_sklearn_loop():
     """ie_pr_thresholds (csrc/pr_curve.cu) against the reference's per-label loop on sklearn's precision_recall_curve
     (py/label_microservice/mlp.py:81-98): identical thresholds, precisions, recalls -- with ties in the scores, labels

@@ -345,6 +345,28 @@ def test_spacy_like_tokenizer_never_loses_characters():
     check()
 
 
+def _check_thresholds_fixture(fn, golden_dir):
+    z = np.load(os.path.join(golden_dir, "thresholds_ref.npz"))
+    for tag in ("a", "b", "c"):
+        thr, prec, rec = fn(z[f"{tag}_scores"], z[f"{tag}_truth"], float(z[f"{tag}_p_thr"]), float(z[f"{tag}_r_thr"]))
+        want = z[f"{tag}_thresholds"]
+        assert [t is None for t in thr] == list(np.isnan(want)), tag
+        np.testing.assert_array_equal(np.array([np.nan if t is None else np.float32(t) for t in thr], dtype=np.float64),
+                                      want)                       # thresholds are score values (f32): exact
+        np.testing.assert_array_equal(np.array(prec), z[f"{tag}_precisions"])
+        np.testing.assert_array_equal(np.array(rec), z[f"{tag}_recalls"])
+    assert np.isnan(z["a_thresholds"]).any() and not np.isnan(z["a_thresholds"]).all()
+
+
+def test_threshold_search_host_restatement_vs_reference_fixture(golden_dir):
+    """Row f-4 pinned on the reference: tests/golden/thresholds_ref.npz holds thresholds / precisions / recalls computed
+    by the reference's own MLPWrapper.find_probability_thresholds loop (py/label_microservice/mlp.py:65-98; generator:
+    make_golden.py thresholds) on preset scores -- ties, a label without positives, excluded labels.  The host restatement
+    (the checker of the device kernel in tests/test_gpu_parity.py) must reproduce them exactly."""
+    from code_intelligence_b200.mlp import pr_thresholds_host
+    _check_thresholds_fixture(pr_thresholds_host, golden_dir)
+
+
 def test_filter_predictions_reference_case():
     """The reference's own test of the label filter (py/label_microservice/repo_specific_model_test.py:10-33): mocked
     probabilities [[.2, .9]] with thresholds .5 / .5 give {"label2": .9}; a falsy threshold removes the label."""
