@@ -9,6 +9,12 @@
 * mlp_ref.npz     -- produced by IMPORTING THE REFERENCE: label_microservice.mlp.MLPWrapper from /root/reference/py
                      (py/label_microservice/mlp.py:56-63) around a fitted sklearn MLPClassifier; stores coefs_,
                      intercepts_, inputs and MLPWrapper.predict_probabilities outputs.
+* thresholds_ref.npz (`make_golden.py thresholds`) -- the reference's MLPWrapper.find_probability_thresholds (mlp.py:65-98)
+                     executed on preset scores.
+* reference_driver.npz (`make_golden.py driver`) -- the reference's OWN bulk driver, pooling and single-issue code
+                     (py/code_intelligence/inference.py: df_to_embedding, batch_seq_pool, get_pooled_features) executed
+                     around the CPU oracle's nn.LSTM stack (stand-ins only for the absent third-party imports).
+* tokenizer_ref_notebook.json -- token strings the reference's pipeline printed in its notebooks (hand-collected).
 """
 import os
 import sys
@@ -116,6 +122,101 @@ def threshold_fixture():
         print('thresholds', tag, int(np.isnan(thr).sum()), 'of', L, 'labels excluded')
     np.savez_compressed(os.path.join(HERE, 'thresholds_ref.npz'), **out)
 
+
+def reference_driver_fixture():
+    """Outputs of the reference's OWN bulk driver and pooling code (py/code_intelligence/inference.py:
+    InferenceWrapper.df_to_embedding :138-229, batch_seq_pool :232-263, get_pooled_features :74-92) run in this
+    container: the module is imported with stand-ins for its absent third-party imports (fastai, mdparse, more_itertools
+    -- none of them takes part in the arithmetic of these functions), the text -> ids step is fed the numericalised docs
+    directly, `.cuda()` is the identity, and `self.encoder` is the CPU oracle's stack of torch nn.LSTM (reset() + forward(x)
+    -> (raw_outputs, outputs) like fastai's AWD_LSTM).  Everything else -- the batch-size rule, the length sort, pad_sequence,
+    _forward_pass, batch_seq_pool, the OOM halving, the un-sort -- is the reference's code, executed."""
+    import types
+    import pandas as pd
+    from oracle import awd_lstm_ref as R
+
+    def mod(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        sys.modules[name] = m
+        return m
+    current = {}
+    mod('more_itertools', chunked=lambda it, n: [list(it)[i:i + n] for i in range(0, len(list(it)), n)])
+    mod('mdparse'); mod('mdparse.parser', transform_pre_rules=[], compose=lambda fs: (lambda x: x))
+    mod('fastai'); mod('fastai.text'); mod('fastai.text.transform', defaults=types.SimpleNamespace(text_pre_rules=[]))
+    mod('fastai.core', PathOrStr=str, parallel=None); mod('fastai.basic_train', load_learner=None)
+    mod('fastai.text.data', TokenizeProcessor=type('TokenizeProcessor', (), {}))
+
+    class FakeLMDB:
+        @staticmethod
+        def from_df(**kw):
+            items = current['docs']
+            return types.SimpleNamespace(valid_dl=types.SimpleNamespace(x=types.SimpleNamespace(items=items)))
+    sys.modules['fastai.text'].TextLMDataBunch = FakeLMDB
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    sys.path.insert(0, '/root/reference/py')
+    from code_intelligence.inference import InferenceWrapper as RefWrapper
+
+    cfg = (2, 32, 48, 300)           # n_layers, emb_sz, n_hid, vocab
+    ref = R.make_encoder(31, cfg[3], cfg[1], cfg[2], cfg[0], scale=2.0)
+
+    class EncoderStub:                # fastai AWD_LSTM surface used by the reference: reset(), forward(x) -> (raw, out)
+        def __init__(self, fail_above=None):
+            self.fail_above, self.calls = fail_above, []
+
+        def reset(self):
+            pass
+
+        def forward(self, x):
+            self.calls.append(tuple(x.shape))
+            if self.fail_above is not None and x.shape[0] > self.fail_above:
+                raise RuntimeError('CUDA out of memory (stub)')
+            with torch.no_grad():
+                h = ref.encoder(x)
+                outs = []
+                for rnn in ref.rnns:
+                    h, _ = rnn(h)
+                    outs.append(h)
+            return outs, outs
+
+    out = {}
+    for tag, n, max_len, bs, fail_above in [('a', 57, 40, 100, None), ('b', 130, 25, 100, None), ('c', 300, 20, 16, 5)]:
+        docs = R.synthetic_ids(n, max_len, seed=100 + n, vocab_sz=cfg[3], min_len=1)
+        current['docs'] = [np.asarray(d, dtype=np.int64) for d in docs]
+        w = object.__new__(RefWrapper)
+        w.encoder = EncoderStub(fail_above)
+        w.pad_idx = 1
+        w.path = None; w.model_tokenizer = None; w.vocab = None
+        w.process_df = lambda df: df
+        df = pd.DataFrame({'title': [''] * n, 'body': [''] * n})
+        emb = w.df_to_embedding(df, bs=bs)
+        assert emb.shape == (n, 3 * cfg[1])
+        lens = np.array([len(d) for d in docs])
+        out[f'{tag}_ids'] = np.concatenate(current['docs']).astype(np.int32)
+        out[f'{tag}_lengths'] = lens.astype(np.int32)
+        out[f'{tag}_bs'] = np.int64(bs)
+        out[f'{tag}_fail_above'] = np.int64(-1 if fail_above is None else fail_above)
+        out[f'{tag}_expected'] = emb.astype(np.float32)
+        out[f'{tag}_batches_seen'] = np.array([c[0] for c in w.encoder.calls], dtype=np.int64)
+        print('reference driver', tag, emb.shape, 'forward calls', len(w.encoder.calls), 'batch sizes', sorted(set(c[0] for c in w.encoder.calls)))
+    # batch_seq_pool and get_pooled_features on their own
+    rng = np.random.default_rng(5)
+    seq = rng.standard_normal((7, 11, 6)).astype(np.float32)
+    lens = np.array([11, 1, 5, 11, 3, 2, 9])
+    out['pool_seq'] = seq; out['pool_lengths'] = lens.astype(np.int32)
+    out['pool_expected'] = RefWrapper.batch_seq_pool(seq, lens).astype(np.float32)
+    w = object.__new__(RefWrapper)
+    w.encoder = EncoderStub()
+    one = np.asarray(R.synthetic_ids(1, 23, seed=9, vocab_sz=cfg[3], min_len=23)[0], dtype=np.int64)
+    w.numericalize_one = lambda x: torch.as_tensor(one)[None, :]
+    out['single_ids'] = one.astype(np.int32)
+    out['single_expected'] = w.get_pooled_features('ignored').detach().numpy().astype(np.float32)
+    out['cfg'] = np.array(cfg, dtype=np.int64); out['seed'] = np.int64(31); out['scale'] = np.float64(2.0)
+    np.savez_compressed(os.path.join(HERE, 'reference_driver.npz'), **out)
+
+
+if __name__ == '__main__' and len(sys.argv) == 2 and sys.argv[1] == 'driver':
+    reference_driver_fixture()
 
 if __name__ == '__main__' and len(sys.argv) == 2 and sys.argv[1] == 'thresholds':
     threshold_fixture()

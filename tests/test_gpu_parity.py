@@ -635,6 +635,24 @@ def test_inference_wrapper_surface(tmp_path):
         wp.encoder.close()
 
 
+def test_bulk_api_vs_the_reference_driver_output(golden_dir, monkeypatch):
+    """The CUDA path through its public bulk API against arrays the REFERENCE'S OWN df_to_embedding / batch_seq_pool
+    code returned (tests/golden/reference_driver.npz; executed in the build container around the CPU oracle's nn.LSTM
+    stack, make_golden.py driver): 57 / 130 / 300 ragged issues, the reference's batch-size rule, its OOM halving."""
+    from test_host_logic import _driver_fixture
+    z, cases = _driver_fixture(golden_dir)
+    n_layers, emb_sz, n_hid, vocab = [int(v) for v in z["cfg"]]
+    ref = R.make_encoder(int(z["seed"]), vocab, emb_sz, n_hid, n_layers, scale=float(z["scale"]))
+    enc = _make((n_layers, emb_sz, n_hid, vocab), ref.export_weights(), monkeypatch)
+    for tag, c in cases.items():
+        got = enc.encode_id_list(c["docs"], bs=c["bs"])
+        m = _assert_parity(got, c["expected"], rel_l2_max=REL_L2_MAX_SCALED)
+        print("reference driver", tag, m)
+    one = z["single_ids"].astype(np.int64)
+    _assert_parity(enc.encode_ids(one[None, :]), z["single_expected"], rel_l2_max=REL_L2_MAX_SCALED)
+    enc.close()
+
+
 # ------------------------------------------------------------------------------------------------ MLP head
 @pytest.mark.parametrize("tag", ["small", "prod"])
 def test_mlp_head_vs_reference_fixture(golden_dir, tag):
