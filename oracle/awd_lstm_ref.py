@@ -23,8 +23,13 @@ Eval-mode fastai semantics (restated from fastai 1.0.53 source knowledge): RNNDr
 EmbeddingDropout / WeightDropout are the identity when ``not training``; the LSTM layer dims follow
 ``in_0=emb_sz, in_l=n_hid, out_l=n_hid (l<L-1), out_{L-1}=emb_sz``.
 
-PARITY STATUS: "parity unpinned" by the reference's own tests -- the reference has no test files and no
-usable golden vectors for this path.  The oracle is pinned instead by (i) the
+PARITY STATUS: the arithmetic core is "parity unpinned" by the reference's own tests -- the reference has no test
+files and no usable golden vectors for this path, and fastai's AWD_LSTM.forward cannot be executed
+here; that it equals this stack of nn.LSTM in eval mode is restated, not run.  Everything AROUND that core is pinned on
+reference code executed in the build container: tests/golden/reference_driver.npz holds what the reference's own
+df_to_embedding / batch_seq_pool / get_pooled_features (py/code_intelligence/inference.py:74-92,138-263) returned when
+run around this module's nn.LSTM stack (tests/golden/make_golden.py driver), and encode_bulk / batch_seq_pool /
+encode_single below are checked against it (tests/test_host_logic.py).  The oracle is further pinned by (i) the
 reference's portable invariant bulk == single within atol 1e-5
 (Issue_Embeddings/notebooks/04b_Inference-Batch.ipynb:369), checked in tests/test_oracle.py, (ii) an
 independent explicit-loop numpy LSTM (oracle/lstm_numpy.py) and (iii) committed golden vectors generated
