@@ -156,6 +156,10 @@ def reference_driver_fixture():
     torch.Tensor.cuda = lambda self, *a, **k: self
     sys.path.insert(0, '/root/reference/py')
     from code_intelligence.inference import InferenceWrapper as RefWrapper
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('flask_app_inference', '/root/reference/Issue_Embeddings/flask_app/inference.py')
+    fi = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(fi)          # the flask_app copy of the wrapper (df_to_emb, FI:136-212)
 
     cfg = (2, 32, 48, 300)           # n_layers, emb_sz, n_hid, vocab
     ref = R.make_encoder(31, cfg[3], cfg[1], cfg[2], cfg[0], scale=2.0)
@@ -198,6 +202,15 @@ def reference_driver_fixture():
         out[f'{tag}_fail_above'] = np.int64(-1 if fail_above is None else fail_above)
         out[f'{tag}_expected'] = emb.astype(np.float32)
         out[f'{tag}_batches_seen'] = np.array([c[0] for c in w.encoder.calls], dtype=np.int64)
+        if fail_above is None:        # Issue_Embeddings/flask_app/inference.py:df_to_emb (chunked batches, no OOM loop)
+            wf = object.__new__(fi.InferenceWrapper)
+            wf.encoder = EncoderStub(None)
+            wf.pad_idx = 1
+            wf.path = None; wf.model_tokenizer = None; wf.vocab = None
+            wf.process_df = lambda df: df
+            emb_fi = wf.df_to_emb(df, bs=bs)
+            out[f'{tag}_expected_flask_app'] = emb_fi.astype(np.float32)
+            print('  flask_app df_to_emb vs py/code_intelligence df_to_embedding: max abs diff', float(np.abs(emb_fi - emb).max()))
         print('reference driver', tag, emb.shape, 'forward calls', len(w.encoder.calls), 'batch sizes', sorted(set(c[0] for c in w.encoder.calls)))
     # batch_seq_pool and get_pooled_features on their own
     rng = np.random.default_rng(5)

@@ -377,6 +377,8 @@ def test_bulk_loop_and_pooling_vs_the_reference_driver(golden_dir):
         np.testing.assert_allclose(got, c["expected"], rtol=0, atol=2e-6, err_msg=tag)
         if c["fail_above"] < 0:      # the oracle's own restatement of the driver (what the GPU tests are checked against)
             np.testing.assert_allclose(R.encode_bulk(ref, c["docs"], bs=c["bs"]), c["expected"], rtol=0, atol=2e-6)
+            # ... and the flask_app copy of the driver (Issue_Embeddings/flask_app/inference.py:136-212), also executed
+            np.testing.assert_allclose(got, z[f"{tag}_expected_flask_app"], rtol=0, atol=2e-6)
     # pooling and the single-issue path on their own
     np.testing.assert_array_equal(InferenceWrapper.batch_seq_pool(z["pool_seq"], z["pool_lengths"]), z["pool_expected"])
     np.testing.assert_array_equal(R.batch_seq_pool(z["pool_seq"], z["pool_lengths"]), z["pool_expected"])
