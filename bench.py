@@ -432,6 +432,9 @@ def main():
             "e2e": {"value": e2e_value, "unit": "issues/s", "h2d_bytes_per_step": B * T * 8 + B * 4,
                     "d2h_bytes_per_step": world * B * 3 * EMB * 4,
                     "api": "bulk.encode_bulk_distributed(host id lists) -> np.ndarray (N, 2400) on rank 0",
+                    "note": "host packing and H2D run under the previous batch's kernels and the result leaves through "
+                            "page-locked memory, so e2e tracks `value` to within the +-2 % clock variation between the two "
+                            "arms (it can land on either side)",
                     "breakdown_ms": e2e_breakdown},
             "single_batch": {"value": single_value, "unit": "issues/s", "ms_per_step": ms_single / K,
                              "note": "same measurement with one batch of 256 per launch"},

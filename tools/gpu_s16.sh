@@ -20,5 +20,6 @@ try:
     print('extra', json.dumps(d['extra'])[:2600]); print('cpu', d.get('cpu_baseline'))
 except Exception as e: print('no line', e)
 PY
+if [ "${SKIP_SWEEP:-0}" = "1" ]; then exit 0; fi
 echo "== seq_len sweep (configs[2])"
 timeout 900 python tools/sweep_seq_len.py > $O/sweep_$TAG.jsonl 2> $O/sweep_$TAG.err; echo "rc=$?"; cat $O/sweep_$TAG.jsonl | cut -c1-420
