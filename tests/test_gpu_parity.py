@@ -696,6 +696,41 @@ def test_mlp_wrapper_matches_sklearn():
     np.testing.assert_allclose(w.predict_probabilities(Xt), clf.predict_proba(Xt), atol=5e-3)
 
 
+def test_reference_test_mlp_cases_on_the_gpu_wrapper():
+    """The reference's own unit tests of the head (Label_Microservice/tests/test_mlp.py:7-57), body for body, with
+    code_intelligence_b200.mlp.MLPWrapper (sklearn fit, GPU predict_proba + ie_pr_thresholds) in place of
+    label_microservice.mlp.MLPWrapper."""
+    import warnings
+    from sklearn.neural_network import MLPClassifier
+    from code_intelligence_b200.mlp import MLPWrapper
+    warnings.simplefilter("ignore")
+    # test_predict_probabilities
+    n_classes, n_samples, embedding_size, random_state = 5, 20, 5, 1234
+    rs = np.random.RandomState(0)
+    X_train = rs.rand(n_samples, embedding_size)
+    y_train = rs.choice([0, 1], size=(n_samples, n_classes))
+    X_test = rs.rand(n_samples, embedding_size)
+    mlp_clf = MLPClassifier(random_state=random_state)
+    mlp_clf.fit(X_train, y_train)
+    mlp_clf_pred = mlp_clf.predict_proba(X_test)
+    mlp_wrap = MLPWrapper(clf=mlp_clf)
+    mlp_wrap.fit(X_train, y_train)
+    mlp_wrap_pred = mlp_wrap.predict_probabilities(X_test)
+    assert mlp_clf_pred.all() == mlp_wrap_pred.all()                         # the reference's (weak) assertion ...
+    np.testing.assert_allclose(mlp_wrap_pred, mlp_clf_pred, atol=5e-3)       # ... and what it means
+    # test_find_probability_thresholds
+    X = np.array([[0.1, 0.1], [0.2, 0.2], [0.3, 0.3], [0.4, 0.4], [0.5, 0.5], [0.6, 0.6]])
+    y = np.array([[1, 0, 0], [1, 0, 0], [0, 1, 0], [0, 1, 0], [0, 0, 1], [0, 0, 1]])
+    precision_threshold, recall_threshold = 0.7, 0.5
+    mlp_wrap = MLPWrapper(clf=MLPClassifier(random_state=random_state), precision_threshold=precision_threshold,
+                          recall_threshold=recall_threshold)
+    mlp_wrap.find_probability_thresholds(X, y)
+    thresholds = mlp_wrap.probability_thresholds
+    precision_0, recall_0 = mlp_wrap.precisions[0], mlp_wrap.recalls[0]
+    assert not thresholds[1] and not thresholds[2] and \
+        precision_0 >= precision_threshold and recall_0 >= recall_threshold
+
+
 def test_threshold_search_on_device_vs_reference_fixture(golden_dir):
     """ie_pr_thresholds against the thresholds / precisions / recalls the reference's own
     MLPWrapper.find_probability_thresholds computed (tests/golden/thresholds_ref.npz, make_golden.py thresholds)."""
