@@ -7,6 +7,8 @@ profiles/README.md "The kernel runs at the board's power cap").
     cublas            : torch.matmul bf16 8192^3 (the driver's MEASURED_PEAKS recipe)
     enc[:K=V[+K=V]]   : encoder path at max_batch rows x T per call, created under the given development knobs
     enc256[:...]      : same with 256 rows per call (one batch per launch)
+    PROBE_IDS=seq|zipf: token ids whose rows of the per-token table are neighbours / follow a Zipf law (default: uniform
+                        random ids, the worst case for the table's DRAM locality: layer 0 then runs ~3 ms slower per call)
 Reports, per workload: median SM clock / board power (nvidia-smi), TFLOP/s, pJ/FLOP, the phase times of the last call
 and the SM clock each layer's recurrent kernel saw (clock64 / globaltimer stamps inside the kernel).
 """
@@ -86,7 +88,6 @@ def run(what, seconds, T):
         if os.environ.get("PROBE_IDS") == "seq":    # neighbouring rows read neighbouring rows of the per-token table
             ids = ((torch.arange(B, device="cuda")[:, None] + 257 * torch.arange(T, device="cuda")[None, :]) % 59000 + 2).to(torch.int64)
         elif os.environ.get("PROBE_IDS") == "zipf":  # a few hot tokens, like text
-            z = torch.distributions.Zipf(torch.tensor(1.1)).sample((B, T)) if hasattr(torch.distributions, "Zipf") else None
             w = 1.0 / torch.arange(1, 59999, dtype=torch.float64) ** 1.1
             ids = (torch.multinomial(w / w.sum(), B * T, replacement=True).view(B, T) + 2).to(torch.int64).cuda()
         lengths = torch.full((B,), T, dtype=torch.int32, device="cuda")
