@@ -11,6 +11,7 @@ def load(p):
 
 d1 = load(sys.argv[1])
 multi = [load(p) for p in sys.argv[2:]]
+multi_names = [os.path.basename(p) for p in sys.argv[2:]]
 r = d1["roofline"]; ph = r["phase_ms_last_call"]; mhz = r["phase_sm_mhz"]
 nb = d1["config"]["batches_per_launch"]
 rows = nb * 256
@@ -43,8 +44,8 @@ for k in ("mlp_1600", "mlp_2400"):
     m = ex[k]
     rf = m['roofline']
     et.append(f"| MLP head ({k[4:]}→600→600→256), 2^20 rows, device-resident | {m['rows_per_s']/1e6:.0f} M rows/s = {m['labels_per_s']/1e9:.1f} G labels/s ({m['ms']:.2f} ms); {m['tflops']:.0f} TFLOP/s = {rf['frac']:.2f} of the binding ({rf['bound']}) roofline; {m['hbm_gbs']:.0f} GB/s of algorithmic traffic = {rf.get('hbm_frac', rf['frac']):.2f} of the HBM roofline |")
-for dm in multi:
-    et.append(f"| {dm['n_gpus']} GPUs: `value` / `e2e` (bulk API) / var-len strong scaling | {dm['value']:.0f} / {dm['e2e']['value']:.0f} / {dm['extra']['bulk_varlen']['value']:.0f} issues/s (bit-equal to single GPU: {dm['extra']['bulk_varlen']['bit_equal_to_single_gpu']}) |")
+for dm, nm in zip(multi, multi_names):
+    et.append(f"| {dm['n_gpus']} GPUs (`{nm}`): `value` / `e2e` (bulk API) / var-len strong scaling | {dm['value']:.0f} / {dm['e2e']['value']:.0f} / {dm['extra']['bulk_varlen']['value']:.0f} issues/s (bit-equal to single GPU: {dm['extra']['bulk_varlen']['bit_equal_to_single_gpu']}) |")
 cb = d1.get("cpu_baseline")
 if cb:
     et.append(f"| CPU oracle on the box ({cb['cores']} threads) | {cb['value']:.1f} issues/s ({cb['sample']}) |")
