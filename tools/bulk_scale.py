@@ -21,8 +21,16 @@ dev = torch.device("cuda", local)
 if world > 1:
     dist.init_process_group("nccl", device_id=dev)
 from code_intelligence_b200 import IssueEncoder, bulk
-from oracle import awd_lstm_ref as R          # weights only (seeded random init of the reference shape)
-emb, layers = R.make_encoder(1234).export_weights()
+# seeded random-init weights of the reference shape (torch-default ranges; no oracle import in tools that check nothing
+# against it)
+g = torch.Generator().manual_seed(1234)
+dims = [((800 if l == 0 else 2400), (2400 if l != 3 else 800)) for l in range(4)]
+emb = (torch.rand(60000, 800, generator=g) * 0.2 - 0.1).numpy()
+layers = []
+for i_, o_ in dims:
+    k_ = 1.0 / np.sqrt(o_)
+    u = lambda *sh: ((torch.rand(*sh, generator=g) * 2 - 1) * k_).numpy()
+    layers.append(dict(w_ih=u(4 * o_, i_), w_hh=u(4 * o_, o_), b_ih=u(4 * o_), b_hh=u(4 * o_)))
 enc = IssueEncoder(device=local).load_weights(emb, layers)
 rng = np.random.default_rng(4321)              # the same global list on every rank, as the API expects
 t0 = time.perf_counter()
