@@ -246,10 +246,12 @@ def test_bench_clock_sampler_summary():
     assert bench.ClockSampler.summarise([])["sm_mhz"] is None
 
 
-def _rot_schedule_model(T, ng, tiles, P, mma, lat, slots=2):
+def _rot_schedule_model(T, ng, tiles, P, mma, lat, slots=2, pre=0.0):
     """Event model of csrc/lstm_layer.cu's schedule: item n = t*C + g*tiles + j (C = ng*tiles) runs on CTA pair n % P, pairs
     walk their items in increasing n; an item's MMAs start when the pair is free, every item of (t-1, g) has been
     published (its MMA end + lat) and the pair's item `slots` positions back has left its TMEM slot (MMA end + lat).
+    `pre`: MMA time of the item that does NOT depend on (t-1, g) -- the fused input projection of the last layer (FUSE):
+    it starts as soon as the pair and the TMEM slot are free, only the remaining `mma` waits for the counter.
     Returns (makespan, items seen, True if every dependency had a smaller index)."""
     C, total = ng * tiles, T * ng * tiles
     end, pub, cnt, tile_pub, pair_free = {}, {}, {}, {}, [0.0] * P
@@ -260,13 +262,14 @@ def _rot_schedule_model(T, ng, tiles, P, mma, lat, slots=2):
         g, j = divmod(c, tiles)
         seen.add((t, g, j))
         start = pair_free[p]
+        if k >= slots:
+            start = max(start, end[n - slots * P] + lat)
+        start += pre                            # the dependency-free part runs first
         if t > 0:
             if (t - 1, g) not in pub:           # some tile of (t-1, g) has an index >= n: the order argument would break
                 ordered = False
                 break
             start = max(start, pub[(t - 1, g)])
-        if k >= slots:
-            start = max(start, end[n - slots * P] + lat)
         end[n] = pair_free[p] = start + mma
         tile_pub[(t, g)] = max(tile_pub.get((t, g), 0.0), end[n] + lat)
         cnt[(t, g)] = cnt.get((t, g), 0) + 1
@@ -288,6 +291,25 @@ def test_rotating_schedule_model():
     per_step = {ng: _rot_schedule_model(T, ng, 38, 74, mma, lat)[0] / T / ng for ng in (3, 5)}
     assert per_step[5] <= 1.02 * ideal, per_step
     assert per_step[3] >= 1.15 * ideal, per_step          # 114 items per timestep: the dependency latency shows
+
+
+def test_fused_last_layer_hides_its_step_chain_in_the_model():
+    """Why the last layer's input projection rides its recurrent K loop (csrc/lstm_layer.cu FUSE): with
+    13 tiles x 5 batches = 65 items per timestep on 74 pairs every pair has at most one item per timestep, so the hoisted
+    form is bound by the step chain (MMA + visibility latency per timestep) and the projection GEMM comes on top; with the
+    38 dependency-free k-blocks in front of the 13 recurrent ones the chain hides behind the item itself and the layer
+    runs at the rate of its MMA stream (65 / 74 of a pair per timestep).  Times in units of one k-block."""
+    T, ng, tiles, P = 64, 5, 13, 74
+    rec, pre, lat = 13.0, 38.0, 22.0          # k-blocks; visibility latency ~ epilogue + publish + counter + first tile
+    hoisted = _rot_schedule_model(T, ng, tiles, P, mma=rec, lat=lat)[0] / T
+    fused, n_items, ordered = _rot_schedule_model(T, ng, tiles, P, mma=rec, lat=lat, pre=pre)
+    fused /= T
+    assert ordered and n_items == T * ng * tiles
+    assert hoisted >= 0.95 * (rec + lat)                         # chain-bound: one MMA phase + one latency per timestep
+    gemm_equiv = pre * ng * tiles / P                            # the hoisted projection at full rate, per timestep
+    stream = (pre + rec) * ng * tiles / P                        # all 51 k-blocks of the 65 items on 74 pairs
+    assert fused <= 1.12 * stream, (fused, stream)               # MMA-stream-bound, chain hidden
+    assert fused <= 0.80 * (hoisted + gemm_equiv), (fused, hoisted, gemm_equiv)
 
 
 def test_bulk_loop_coalesces_reference_batches():
